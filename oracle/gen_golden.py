@@ -1,0 +1,164 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the REFERENCE ITSELF -- run in the build container only.
+
+This script imports the reference's own, unmodified ms_deform_attn_core_pytorch and MSDeformAttn from
+/root/reference (ops/functions/ms_deform_attn_func.py:53-72, ops/modules/ms_deform_attn.py:34-129),
+with the compiled-extension import stubbed (the guard at ms_deform_attn_func.py:21-29 only needs the
+module name to resolve), runs them on CPU in float64 and stores inputs, outputs and autograd gradients.
+/root/reference does not exist on the GPU box, hence the committed fixtures.
+
+Cases follow the reference's only test artefact, ops/test.py:
+  testpy_fwd_double / testpy_fwd_float : seed 3, N,M,D=1,2,2, Lq,L,P=2,2,2, shapes (6,4),(3,2)  (test.py:24-71);
+                                         the RNG draw order of test.py is reproduced, so these are the very
+                                         tensors test.py feeds the CUDA op.
+  testpy_grad_D{30,32,64,71}           : the gradcheck shapes of test.py:74-96 (values + analytic grads)
+plus what test.py does not cover: the S4 level pyramid with D=32, P=4, out-of-range and
+border-straddling sample locations, N>1, and the MSDeformAttn module end to end.
+
+Usage: python oracle/gen_golden.py   (writes tests/golden/, prints a manifest)
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference/models/modeling/pixel_decoder"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def import_reference():
+    sys.modules.setdefault("MultiScaleDeformableAttention", types.ModuleType("MultiScaleDeformableAttention"))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        from ops.functions.ms_deform_attn_func import ms_deform_attn_core_pytorch
+        from ops.modules import MSDeformAttn
+    return ms_deform_attn_core_pytorch, MSDeformAttn
+
+
+def level_start(shapes):
+    return torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+
+
+def run_case(core, value, shapes, loc, attn, grad_out=None):
+    """fp64 forward + autograd backward through the reference's torch path."""
+    v = value.double().clone().requires_grad_(True)
+    l = loc.double().clone().requires_grad_(True)
+    a = attn.double().clone().requires_grad_(True)
+    out = core(v, shapes, l, a)
+    if grad_out is None:
+        grad_out = torch.ones_like(out)
+    out.backward(grad_out.double())
+    return out.detach(), v.grad, l.grad, a.grad
+
+
+def save(name, **arrs):
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()})
+    print("%-28s %8.1f KB" % (name, os.path.getsize(path) / 1024))
+
+
+def draw(N, S, M, D, Lq, L, P):
+    """Same draw order and distributions as test.py:36-39."""
+    value = torch.rand(N, S, M, D) * 0.01
+    loc = torch.rand(N, Lq, M, L, P, 2)
+    attn = torch.rand(N, Lq, M, L, P) + 1e-5
+    attn /= attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    return value, loc, attn
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    core, MSDeformAttn = import_reference()
+    torch.set_num_threads(1)
+
+    # ---- the reference's own test.py, reproduced draw by draw -------------------------------------------
+    N, M, D = 1, 2, 2
+    Lq, L, P = 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    torch.manual_seed(3)
+    for tag in ("double", "float"):  # test.py runs the double check first, then the float check
+        value, loc, attn = draw(N, S, M, D, Lq, L, P)
+        out, gv, gl, ga = run_case(core, value, shapes, loc, attn)
+        out32 = core(value, shapes, loc, attn)  # what test.py:62 computes in float
+        save("testpy_fwd_" + tag, value=value, shapes=shapes, start=level_start(shapes), loc=loc, attn=attn,
+             out=out, out_f32path=out32, grad_value=gv, grad_loc=gl, grad_attn=ga, im2col_step=2)
+    for ch in (30, 32, 64, 71):  # test.py:95 (the 1025/2048/3096 widths are generated procedurally in tests)
+        value, loc, attn = draw(N, S, M, ch, Lq, L, P)
+        out, gv, gl, ga = run_case(core, value, shapes, loc, attn)
+        save("testpy_grad_D%d" % ch, value=value, shapes=shapes, start=level_start(shapes), loc=loc, attn=attn,
+             out=out, grad_value=gv, grad_loc=gl, grad_attn=ga, im2col_step=2)
+
+    # ---- S4 pyramid (configs/avs_s4: 224x224, strides 32/16/8), D=32, P=4 ----------------------------------
+    shapes = torch.as_tensor([(7, 7), (14, 14), (28, 28)], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    g = torch.Generator().manual_seed(1234)
+    N, M, D, Lq, L, P = 1, 2, 32, 96, 3, 4
+    value = torch.rand(N, S, M, D, generator=g) * 0.01
+    attn = torch.rand(N, Lq, M, L, P, generator=g) + 1e-5
+    attn /= attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    grad_out = torch.rand(N, Lq, M * D, generator=g)
+    # (a) locations as in test.py
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g)
+    out, gv, gl, ga = run_case(core, value, shapes, loc, attn, grad_out)
+    save("s4pyr_unit", value=value, shapes=shapes, start=level_start(shapes), loc=loc, attn=attn, grad_out=grad_out,
+         out=out, grad_value=gv, grad_loc=gl, grad_attn=ga, im2col_step=128)
+    # (b) edge set: locations in [-0.3, 1.3] -> out-of-range samples and border-straddling footprints
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.6 - 0.3
+    out, gv, gl, ga = run_case(core, value, shapes, loc, attn, grad_out)
+    save("s4pyr_edge", value=value, shapes=shapes, start=level_start(shapes), loc=loc, attn=attn, grad_out=grad_out,
+         out=out, grad_value=gv, grad_loc=gl, grad_attn=ga, im2col_step=128)
+
+    # ---- non-square levels, odd sizes, N=3, P=3, L=4 --------------------------------------------------------
+    shapes = torch.as_tensor([(5, 9), (3, 4), (2, 2), (1, 1)], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    N, M, D, Lq, L, P = 3, 3, 8, 17, 4, 3
+    value = torch.randn(N, S, M, D, generator=g)
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g) * 1.4 - 0.2
+    attn = torch.randn(N, Lq, M, L, P, generator=g)  # unnormalised, signed: the op does not require a softmax
+    grad_out = torch.randn(N, Lq, M * D, generator=g)
+    out, gv, gl, ga = run_case(core, value, shapes, loc, attn, grad_out)
+    save("ragged_levels", value=value, shapes=shapes, start=level_start(shapes), loc=loc, attn=attn, grad_out=grad_out,
+         out=out, grad_value=gv, grad_loc=gl, grad_attn=ga, im2col_step=3)
+
+    # ---- MSDeformAttn module (the caller contract, ops/modules/ms_deform_attn.py:86-129) -----------------------
+    torch.manual_seed(7)
+    shapes = torch.as_tensor([(4, 4), (8, 8), (16, 16)], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    N, C = 2, 32
+    mod = MSDeformAttn(d_model=C, n_levels=3, n_heads=2, n_points=4).double()
+    with torch.no_grad():  # move off the zero-init so offsets / weights depend on the query
+        mod.sampling_offsets.weight.normal_(0, 0.05)
+        mod.attention_weights.weight.normal_(0, 0.5)
+        mod.attention_weights.bias.normal_(0, 0.5)
+    query = torch.randn(N, S, C).double()
+    src = torch.randn(N, S, C).double()
+    ref2 = torch.rand(N, S, 3, 2).double()
+    ref4 = torch.cat([ref2, torch.rand(N, S, 3, 2).double() * 0.3 + 0.05], -1)
+    mask = torch.rand(N, S) < 0.1
+    state = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    start = level_start(shapes)
+    y2 = mod(query, ref2, src, shapes, start, None)        # CPU -> bare-except torch path (ms_deform_attn.py:123-125)
+    y2m = mod(query, ref2, src, shapes, start, mask)
+    y4 = mod(query, ref4, src, shapes, start, None)
+    save("module_small", query=query, src=src, ref2=ref2, ref4=ref4, mask=mask, shapes=shapes, start=start,
+         y2=y2.detach(), y2_masked=y2m.detach(), y4=y4.detach(),
+         **{"sd_" + k.replace(".", "__"): v for k, v in state.items()})
+    fresh = MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4)
+    save("module_init_256", offsets_bias=fresh.sampling_offsets.bias.detach(),
+         offsets_weight_absmax=fresh.sampling_offsets.weight.detach().abs().max(),
+         attn_weight_absmax=fresh.attention_weights.weight.detach().abs().max(),
+         attn_bias_absmax=fresh.attention_weights.bias.detach().abs().max(),
+         value_bias_absmax=fresh.value_proj.bias.detach().abs().max(),
+         output_bias_absmax=fresh.output_proj.bias.detach().abs().max(),
+         value_weight_bound=np.sqrt(6.0 / (256 + 256)),
+         n_params=sum(p.numel() for p in fresh.parameters()))
+
+
+if __name__ == "__main__":
+    main()
