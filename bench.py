@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- MSDeformAttn core fwd+bwd throughput on B200 (BASELINE.json configs[1]), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype fp32|bf16] [--frames F]
+
+A "step" is one forward + one backward of the MSDeformAttn core over one batch of synthetic S4-shaped frames
+(N=40 frames = 8 clips x 5 frames, 3 levels 7x7/14x14/28x28, 8 heads, 4 points, d_model 256, Lq = S = 1029),
+inputs drawn like the reference's own test (ops/test.py:36-39).  `value` is frames/s through fwd+bwd with inputs
+resident in HBM; `e2e` is the same metric through the host-buffer entry point (pinned host tensors -> H2D -> kernels
+-> D2H of every result, all inside the timed region).  N>1: one process per GPU (torchrun), every rank runs its own
+40-frame batch (weak scaling, the op has no cross-frame dependency and no collective); time = max over ranks.
+
+--impl reference times the reference's CPU implementation of the same path (ms_deform_attn_core_pytorch,
+restated in oracle/core_pytorch.py because /root/reference does not exist on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+S4_SHAPES = [(7, 7), (14, 14), (28, 28)]
+M, D, L, P = 8, 32, 3, 4
+S = sum(h * w for h, w in S4_SHAPES)
+LQ = S
+METRIC = "msdeformattn_fwd_bwd_frames_per_s"
+UNIT = "frames/s"
+N_SETS = 4  # rotating input/output sets so that every step starts cold in L2
+
+
+def algorithmic_bytes(n_frames, val_bytes, meta_bytes):
+    """every input read once + every output written once, per pass."""
+    value = n_frames * S * M * D * val_bytes
+    loc = n_frames * LQ * M * L * P * 2 * meta_bytes
+    attn = n_frames * LQ * M * L * P * meta_bytes
+    out = n_frames * LQ * M * D * val_bytes
+    fwd = value + loc + attn + out
+    bwd = (value + loc + attn) + out + value + (loc + attn)  # inputs + grad_out + grad_value + grad_loc + grad_attn
+    return fwd, bwd
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def synth_inputs(torch, n_frames, seed, dtype, loc_dtype, device, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    value = torch.rand(n_frames, S, M, D, generator=g) * 0.01
+    loc = torch.rand(n_frames, LQ, M, L, P, 2, generator=g)
+    attn = torch.rand(n_frames, LQ, M, L, P, generator=g) + 1e-5
+    attn /= attn.sum(-1, keepdim=True).sum(-2, keepdim=True)
+    gout = torch.rand(n_frames, LQ, M * D, generator=g)
+    ts = [value.to(dtype), loc.to(loc_dtype), attn.to(loc_dtype), gout.to(dtype)]
+    if device is not None:
+        return [t.to(device) for t in ts]
+    return [t.pin_memory() if pin else t for t in ts]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed regions run (B200_PROFILING.md 'clocks line')."""
+    FIELDS = ("uuid,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.uuid = uuid
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 9 and (self.uuid is None or self.uuid in parts[0]):
+                self.rows.append((time.time(), parts))
+
+    def stop(self, windows):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        rows = [p for t, p in self.rows if any(a <= t <= b for a, b in windows)] or [p for _, p in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(p[1]) for p in rows if num(p[1]) is not None]
+        reasons = set()
+        for p in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max((num(p[3]) or 0.0) for p in rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def time_cpu_port(torch, n_frames, steps, warmup, threads=None):
+    """fwd+bwd of the reference's CPU path (restated: oracle/core_pytorch.py <- ms_deform_attn_func.py:53-72) in fp32."""
+    from oracle.core_pytorch import msda_core_pytorch
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    value, loc, attn, gout = synth_inputs(torch, n_frames, 3, torch.float32, torch.float32, None)
+    shapes = torch.tensor(S4_SHAPES, dtype=torch.long)
+    value.requires_grad_(True)
+    loc.requires_grad_(True)
+    attn.requires_grad_(True)
+
+    def step():
+        value.grad = loc.grad = attn.grad = None
+        out = msda_core_pytorch(value, shapes, loc, attn)
+        out.backward(gout)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return dt / steps, threads
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_frames = args.frames
+    # bounded sample: shrink the batch until one fwd+bwd takes <= ~1.5 s on this host
+    probe, threads = time_cpu_port(torch, min(n_frames, 5), 1, 1)
+    per_frame = probe / min(n_frames, 5)
+    sample = n_frames
+    while sample > 5 and per_frame * sample > 1.5:
+        sample //= 2
+    sec, threads = time_cpu_port(torch, sample, args.steps, args.warmup)
+    fps = sample / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(n_frames, "f32"),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d of %d frames per step, fwd+bwd, torch %s CPU grid_sample path (oracle/core_pytorch.py)" % (sample, n_frames, torch.__version__)},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n_frames, dtype):
+    return {"workload": "standalone MSDeformAttn core fwd+bwd, AVSBench S4 shape (BASELINE.json configs[1])",
+            "frames_per_gpu": n_frames, "levels": S4_SHAPES, "heads": M, "points": P, "head_dim": D, "queries": LQ,
+            "im2col_step": 128, "inputs": "value=U*0.01, loc=U[0,1), attn=normalised U (reference ops/test.py:36-39), seed 3",
+            "l2": "%d rotating input/output sets (> 126 MB L2 each step cold)" % N_SETS, "value_dtype": dtype}
+
+
+# ------------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:  # convenience: relaunch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import combo_avs_b200 as pkg
+    from combo_avs_b200.host_api import HostPipeline
+
+    if args.fwd_variant:
+        pkg.select_variant("forward", args.fwd_variant)
+    if args.bwd_variant:
+        pkg.select_variant("backward", args.bwd_variant)
+    dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
+    loc_dtype = torch.float32 if args.dtype == "fp32" or args.loc_dtype == "fp32" else torch.bfloat16
+    nF = args.frames
+    shapes = torch.tensor(S4_SHAPES, dtype=torch.long, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    sets = [synth_inputs(torch, nF, 3 + i + 100 * rank, dtype, loc_dtype, dev) for i in range(N_SETS)]
+    fwd = pkg.ms_deform_attn_forward
+    bwd = pkg.ms_deform_attn_backward
+
+    def step(i):
+        v, l, a, g = sets[i % N_SETS]
+        out = fwd(v, shapes, start, l, a, 128)
+        return out, bwd(v, shapes, start, l, a, g, 128)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, (t0, time.time())
+
+    uuid = None
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    windows = []
+
+    # ---- the headline: K fwd+bwd steps, inputs resident in HBM ------------------------------------------------------
+    warm = max(args.warmup, 3)
+    l0 = pkg.launch_count()
+    ms_total, w = timed(step, args.steps, warm)
+    launches = (pkg.launch_count() - l0) * args.steps // (args.steps + warm)
+    windows.append(w)
+    ms_step = ms_total / args.steps
+    fps = world * nF / (ms_step * 1e-3)
+
+    # ---- per-kernel durations for the roofline (rank 0's GPU, same rotating sets) --------------------------------------
+    reps = max(args.steps, int(0.4 / max(ms_step * 1e-3, 1e-6)))  # >= ~0.4 s per loop so the clock sampler sees it
+    ms_f, w = timed(lambda i: fwd(sets[i % N_SETS][0], shapes, start, sets[i % N_SETS][1], sets[i % N_SETS][2], 128), reps, 3)
+    windows.append(w)
+    ms_b, w = timed(lambda i: bwd(sets[i % N_SETS][0], shapes, start, sets[i % N_SETS][1], sets[i % N_SETS][2], sets[i % N_SETS][3], 128), reps, 3)
+    windows.append(w)
+    us_f, us_b = ms_f / reps * 1e3, ms_b / reps * 1e3
+    vb, mb = (4 if dtype == torch.float32 else 2), (4 if loc_dtype == torch.float32 else 2)
+    bytes_f, bytes_b = algorithmic_bytes(nF, vb, mb)
+    peak, peak_src = load_peaks()
+    dom = ("backward", bytes_b, us_b) if us_b >= us_f else ("forward", bytes_f, us_f)
+    achieved = dom[1] / (dom[2] * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "kernel": "%s (%s)" % (dom[0], pkg.last_variant(dom[0])), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom[1], "us_per_launch": dom[2],
+                "fwd": {"us": us_f, "bytes": bytes_f, "GBps": bytes_f / us_f / 1e3, "frac": bytes_f / us_f / 1e3 / peak, "variant": pkg.last_variant("forward")},
+                "bwd": {"us": us_b, "bytes": bytes_b, "GBps": bytes_b / us_b / 1e3, "frac": bytes_b / us_b / 1e3 / peak, "variant": pkg.last_variant("backward")},
+                "fwd_bwd": {"us": us_f + us_b, "bytes": bytes_f + bytes_b, "frac": (bytes_f + bytes_b) / (us_f + us_b) / 1e3 / peak}}
+
+    # ---- end to end through the host-buffer API: pinned host inputs -> H2D -> kernels -> D2H of all results ------------
+    host_in = synth_inputs(torch, nF, 3 + 100 * rank, dtype, loc_dtype, None, pin=True)
+    host_out = [torch.empty((nF, LQ, M * D), dtype=dtype).pin_memory(), torch.empty_like(host_in[0]).pin_memory(),
+                torch.empty_like(host_in[1]).pin_memory(), torch.empty_like(host_in[2]).pin_memory()]
+    pipe = HostPipeline(dev, chunk_frames=args.e2e_chunk)
+    xfer = {}
+
+    def e2e_step(i):
+        xfer["h2d"], xfer["d2h"] = pipe.forward_backward(host_in[0], shapes, start, host_in[1], host_in[2], host_in[3], *host_out, 128)
+
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.time()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    t1 = time.time()
+    e2e_s = (t1 - t0) / e2e_steps  # host wall clock: the call returns only when results are on the host
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    windows.append((t0, t1))
+    e2e = {"value": world * nF / e2e_s, "unit": UNIT, "h2d_bytes_per_step": xfer["h2d"], "d2h_bytes_per_step": xfer["d2h"],
+           "ms_per_step": e2e_s * 1e3, "api": "combo_avs_b200.host_api.HostPipeline.forward_backward (pinned host tensors, %d-frame chunks, 3 streams)" % args.e2e_chunk}
+
+    clocks = sampler.stop(windows) if sampler else None
+
+    # ---- CPU baseline beside it (rank 0, single-GPU run only): bounded sample of the same workload ---------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = min(nF, 40)
+        probe, threads = time_cpu_port(torch, 5, 1, 1)
+        iters = max(2, min(10, int(15.0 / max(probe / 5 * sample, 1e-3))))
+        sec, threads = time_cpu_port(torch, sample, iters, 1)
+        cpu = {"value": sample / sec, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d frames x %d fwd+bwd steps, fp32, torch %s CPU path restating ms_deform_attn_core_pytorch (oracle/core_pytorch.py)" % (sample, iters, torch.__version__),
+               "ms_per_step": sec * 1e3}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16",
+                "data": "synthetic", "config": workload_config(nF, args.dtype), "fwd_bwd_us": ms_step * 1e3,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "variants": {"forward": pkg.last_variant("forward"), "backward": pkg.last_variant("backward")}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--loc-dtype", default="fp32", choices=["fp32", "bf16"], help="bf16 runs only: dtype of locations / weights")
+    ap.add_argument("--frames", type=int, default=40, help="frames per GPU per step (S4: 8 clips x 5 frames)")
+    ap.add_argument("--fwd-variant", default=None)
+    ap.add_argument("--bwd-variant", default=None)
+    ap.add_argument("--e2e-chunk", type=int, default=8)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,263 @@
+// msda_api.cu -- the C ABI of libmsda_b200.so (include/msda_b200.h): argument validation, the checks the
+// reference host code makes (ops/src/cuda/ms_deform_attn_cuda.cu:33-57, 98-121), variant selection and dispatch.
+// No torch / ATen types cross this boundary; the caller owns every buffer.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/msda_b200.h"
+#include "msda_kernels.h"
+
+namespace msda {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+namespace {
+
+thread_local char t_error[512] = "";
+thread_local const char *t_last_variant[2] = {"none", "none"};
+
+enum FwdVariant { kFwdAuto = 0, kFwdGeneric, kFwdWarp32, kFwdCount };
+enum BwdVariant { kBwdAuto = 0, kBwdGeneric, kBwdWarp32, kBwdCount };
+const char *const kFwdNames[kFwdCount] = {"auto", "generic", "warp32"};
+const char *const kBwdNames[kBwdCount] = {"auto", "generic", "warp32"};
+std::atomic<int> g_forced[2] = {{0}, {0}};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail((int)e, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int smem_optin = 0;
+    bool ok = false;
+};
+
+// Device properties are immutable: cache them per ordinal (read-only after first use).
+int device_info(int device, DeviceInfo &out)
+{
+    static DeviceInfo cache[64];
+    static std::mutex mu;
+    if (device < 0 || device >= 64) return fail(MSDA_ERR_DIM, "device ordinal %d out of range", device);
+    std::lock_guard<std::mutex> lock(mu);
+    if (!cache[device].ok) {
+        cudaError_t e = cudaDeviceGetAttribute(&cache[device].sm_count, cudaDevAttrMultiProcessorCount, device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(sm count)");
+        e = cudaDeviceGetAttribute(&cache[device].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(smem optin)");
+        int major = 0;
+        e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(cc major)");
+        if (major != 10)
+            return fail((int)cudaErrorNoKernelImageForDevice,
+                        "libmsda_b200 holds sm_100a code only; device %d has compute capability %d.x", device, major);
+        cache[device].ok = true;
+    }
+    out = cache[device];
+    return MSDA_OK;
+}
+
+int elem_size(int dtype) { return dtype == MSDA_F32 ? 4 : dtype == MSDA_BF16 ? 2 : dtype == MSDA_F64 ? 8 : 0; }
+
+int fill_problem(Problem &p, int dtype, int loc_dtype, const void *value, const int64_t *shapes, const int64_t *start,
+                 const void *loc, const void *attn, int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
+                 const int64_t *shapes_host, const int64_t *start_host, int device)
+{
+    if (elem_size(dtype) == 0) return fail(MSDA_ERR_DTYPE, "unknown dtype %d", dtype);
+    if (!((dtype == MSDA_BF16 && (loc_dtype == MSDA_BF16 || loc_dtype == MSDA_F32)) || (dtype != MSDA_BF16 && loc_dtype == dtype)))
+        return fail(MSDA_ERR_DTYPE, "unsupported (dtype=%d, loc_dtype=%d): locations/weights must match value, or be f32 with bf16 values",
+                    dtype, loc_dtype);
+    if (N < 0 || S < 0 || Lq < 0 || M <= 0 || D <= 0 || L <= 0 || P <= 0)
+        return fail(MSDA_ERR_DIM, "bad dimensions N=%d S=%d M=%d D=%d L=%d Lq=%d P=%d", N, S, M, D, L, Lq, P);
+    const long long lim = 0x7fffffffLL;
+    if ((long long)S * M * D > lim || (long long)Lq * M * L * P * 2 > lim || (long long)N * Lq * M > lim / 64)
+        return fail(MSDA_ERR_DIM, "problem too large for 32-bit per-frame indexing");
+    if (im2col_step <= 0) return fail(MSDA_ERR_STEP, "im2col_step must be positive, got %d", im2col_step);
+    const int step = N < im2col_step ? N : im2col_step;
+    if (N > 0 && N % step != 0) return fail(MSDA_ERR_STEP, "batch(%d) must divide im2col_step(%d)", N, step);
+    const bool empty = (N == 0 || Lq == 0);
+    if (!empty && (!value || !shapes || !start || !loc || !attn)) {
+        if (!(S == 0 && !value && shapes && start && loc && attn)) return fail(MSDA_ERR_NULL, "NULL input pointer");
+    }
+    DeviceInfo di;
+    int rc = device_info(device, di);
+    if (rc != MSDA_OK) return rc;
+    p.dtype = dtype;
+    p.loc_dtype = loc_dtype;
+    p.N = N; p.S = S; p.M = M; p.D = D; p.L = L; p.Lq = Lq; p.P = P;
+    p.value = value; p.shapes = shapes; p.start = start; p.loc = loc; p.attn = attn;
+    p.sm_count = di.sm_count;
+    p.smem_optin = di.smem_optin;
+    p.have_host = shapes_host != nullptr && start_host != nullptr && L <= kMaxLevels;
+    if (p.have_host) {
+        long long total = 0;
+        for (int l = 0; l < L; ++l) {
+            const int64_t H = shapes_host[2 * l], W = shapes_host[2 * l + 1];
+            if (H <= 0 || W <= 0 || H > 1 << 20 || W > 1 << 20) return fail(MSDA_ERR_DIM, "level %d has shape %lld x %lld", l, (long long)H, (long long)W);
+            if (start_host[l] < 0 || start_host[l] + H * W > S)
+                return fail(MSDA_ERR_DIM, "level %d (start %lld, %lld x %lld) exceeds S=%d", l, (long long)start_host[l], (long long)H, (long long)W, S);
+            p.table.H[l] = (int)H;
+            p.table.W[l] = (int)W;
+            p.table.start[l] = (int)start_host[l];
+            total += H * W;
+        }
+        (void)total;
+    }
+    return MSDA_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int device)
+    {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev != device) {
+            e = cudaSetDevice(device);
+            switched = e == cudaSuccess;
+        }
+        return e;
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+}  // namespace msda
+
+using namespace msda;
+
+extern "C" {
+
+int msda_version(void) { return MSDA_VERSION; }
+
+const char *msda_last_error(void) { return t_error; }
+
+uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char *msda_variant_names(int pass_)
+{
+    return pass_ == 0 ? "auto,generic,warp32" : "auto,generic,warp32";
+}
+
+const char *msda_last_variant(int pass_) { return (pass_ == 0 || pass_ == 1) ? t_last_variant[pass_] : "none"; }
+
+int msda_select_variant(int pass_, const char *name)
+{
+    if (pass_ != 0 && pass_ != 1) return fail(MSDA_ERR_VARIANT, "pass must be 0 (forward) or 1 (backward)");
+    if (!name) return fail(MSDA_ERR_NULL, "variant name is NULL");
+    const char *const *names = pass_ == 0 ? kFwdNames : kBwdNames;
+    const int count = pass_ == 0 ? (int)kFwdCount : (int)kBwdCount;
+    for (int i = 0; i < count; ++i)
+        if (strcmp(name, names[i]) == 0) {
+            g_forced[pass_].store(i);
+            return MSDA_OK;
+        }
+    return fail(MSDA_ERR_VARIANT, "unknown %s variant '%s' (have: %s)", pass_ == 0 ? "forward" : "backward", name, msda_variant_names(pass_));
+}
+
+int msda_forward(int dtype, int loc_dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const void *sampling_loc, const void *attn_weight, void *output, int N, int S, int M, int D, int L, int Lq, int P,
+                 int im2col_step, const int64_t *shapes_host, const int64_t *level_start_host, int device, void *stream)
+{
+    Problem p;
+    int rc = fill_problem(p, dtype, loc_dtype, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L, Lq,
+                          P, im2col_step, shapes_host, level_start_host, device);
+    if (rc != MSDA_OK) return rc;
+    if (N == 0 || Lq == 0) return MSDA_OK;
+    if (!output) return fail(MSDA_ERR_NULL, "output is NULL");
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    int v = g_forced[0].load();
+    if (v == kFwdAuto) v = warp32_supported(p) ? kFwdWarp32 : kFwdGeneric;
+    if (S == 0) v = kFwdGeneric;
+    switch (v) {
+    case kFwdWarp32:
+        if (!warp32_supported(p)) return fail(MSDA_ERR_VARIANT, "forward variant warp32 needs f32, D=32, L<=%d", kMaxLevels);
+        e = fwd_warp32(p, output, st);
+        break;
+    default:
+        v = kFwdGeneric;
+        e = fwd_generic(p, output, st);
+        break;
+    }
+    t_last_variant[0] = kFwdNames[v];
+    if (e != cudaSuccess) return cuda_fail(e, "msda_forward launch");
+    return MSDA_OK;
+}
+
+size_t msda_backward_workspace_bytes(int dtype, int loc_dtype, int N, int S, int M, int D, int L, int Lq, int P)
+{
+    (void)loc_dtype; (void)L; (void)Lq; (void)P;
+    if (N <= 0 || S <= 0 || M <= 0 || D <= 0) return 0;
+    return bwd_generic_workspace(dtype, N, S, M, D);
+}
+
+int msda_backward(int dtype, int loc_dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                  const void *sampling_loc, const void *attn_weight, const void *grad_output, void *grad_value,
+                  void *grad_sampling_loc, void *grad_attn_weight, int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
+                  const int64_t *shapes_host, const int64_t *level_start_host, void *workspace, size_t workspace_bytes, int device,
+                  void *stream)
+{
+    Problem p;
+    int rc = fill_problem(p, dtype, loc_dtype, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, N, S, M, D, L, Lq,
+                          P, im2col_step, shapes_host, level_start_host, device);
+    if (rc != MSDA_OK) return rc;
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_val = (size_t)N * S * M * D;
+    if (N == 0 || Lq == 0) {  // no samples: grad_value is all zero, the other two are empty
+        if (n_val > 0) {
+            if (!grad_value) return fail(MSDA_ERR_NULL, "grad_value is NULL");
+            e = cudaMemsetAsync(grad_value, 0, n_val * elem_size(dtype), st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_value)");
+        }
+        return MSDA_OK;
+    }
+    if (!grad_output || !grad_sampling_loc || !grad_attn_weight || (n_val > 0 && !grad_value))
+        return fail(MSDA_ERR_NULL, "NULL gradient pointer");
+    const size_t need = msda_backward_workspace_bytes(dtype, loc_dtype, N, S, M, D, L, Lq, P);
+    if (need > 0 && (!workspace || workspace_bytes < need))
+        return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
+
+    BackwardIO io{grad_output, grad_value, grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes};
+    int v = g_forced[1].load();
+    if (v == kBwdAuto) v = warp32_supported(p) ? kBwdWarp32 : kBwdGeneric;
+    if (S == 0) v = kBwdGeneric;
+    switch (v) {
+    case kBwdWarp32:
+        if (!warp32_supported(p)) return fail(MSDA_ERR_VARIANT, "backward variant warp32 needs f32, D=32, L<=%d", kMaxLevels);
+        e = bwd_warp32(p, io, st);
+        break;
+    default:
+        v = kBwdGeneric;
+        e = bwd_generic(p, io, st);
+        break;
+    }
+    t_last_variant[1] = kBwdNames[v];
+    if (e != cudaSuccess) return cuda_fail(e, "msda_backward launch");
+    return MSDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,47 @@
+// msda_kernels.h -- internal launcher interface between msda_api.cu and the kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "msda_common.cuh"
+
+namespace msda {
+
+struct Problem {
+    int dtype, loc_dtype;
+    int N, S, M, D, L, Lq, P;
+    const void *value;
+    const int64_t *shapes;  // device
+    const int64_t *start;   // device
+    const void *loc;
+    const void *attn;
+    bool have_host;    // host mirror of the geometry supplied
+    LevelTable table;  // valid iff have_host
+    int sm_count;
+    int smem_optin;    // max dynamic shared memory per block (opt-in)
+};
+
+struct BackwardIO {
+    const void *grad_out;
+    void *grad_value;
+    void *grad_loc;
+    void *grad_attn;
+    void *workspace;
+    size_t workspace_bytes;
+};
+
+void count_launch(int n = 1);
+
+// generic: any D / L / P, f32 / f64 / bf16 (msda_generic.cu)
+cudaError_t fwd_generic(const Problem &p, void *out, cudaStream_t st);
+cudaError_t bwd_generic(const Problem &p, const BackwardIO &io, cudaStream_t st);
+size_t bwd_generic_workspace(int dtype, int N, int S, int M, int D);
+
+// warp32: D == 32, f32, warp-cooperative gather straight from L1/L2 (msda_warp32.cu)
+bool warp32_supported(const Problem &p);
+cudaError_t fwd_warp32(const Problem &p, void *out, cudaStream_t st);
+cudaError_t bwd_warp32(const Problem &p, const BackwardIO &io, cudaStream_t st);
+
+}  // namespace msda

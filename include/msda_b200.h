@@ -1,0 +1,111 @@
+/*
+ * msda_b200.h -- C ABI of libmsda_b200.so: multi-scale deformable attention core for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for COMBO-AVS's one native extension.  Each entry point replaces one symbol
+ * of the reference's pybind11 module `MultiScaleDeformableAttention`
+ * (/root/reference/models/modeling/pixel_decoder/ops/src/vision.cpp:18-21):
+ *
+ *   msda_forward   <->  ms_deform_attn_forward   (src/ms_deform_attn.h:25-44  -> src/cuda/ms_deform_attn_cuda.cu:25-85)
+ *   msda_backward  <->  ms_deform_attn_backward  (src/ms_deform_attn.h:46-66  -> src/cuda/ms_deform_attn_cuda.cu:88-158)
+ *
+ * Differences from the reference boundary, all deliberate:
+ *   - plain pointers and sizes, no torch/ATen types: the caller allocates every output (torch.empty is enough;
+ *     the library zero-fills whatever the selected kernel needs) and passes the device ordinal and the
+ *     cudaStream_t to run on.  The reference allocates with at::zeros and uses the ambient current stream.
+ *   - every function returns a status (0 ok, <0 argument error, >0 cudaError_t) and records a message readable
+ *     with msda_last_error(); the reference only printf()s launch errors (ms_deform_im2col_cuda.cuh:953-957,1326-1330).
+ *   - bf16 is accepted in addition to the reference's float/double dispatch (ms_deform_attn_cuda.cu:69,139).
+ *   - there is no CPU implementation and no fallback (the reference's CPU entry points are AT_ERROR stubs,
+ *     src/cpu/ms_deform_attn_cpu.cpp:31,44).
+ *
+ * Tensor layouts are the reference's (row-major, contiguous; ms_deform_attn_cuda.cu:45-53):
+ *   value          [N, S, M, D]            dtype
+ *   spatial_shapes [L, 2]  (H_l, W_l)      int64, device memory          (host mirror optional, see below)
+ *   level_start    [L]                     int64, device memory
+ *   sampling_loc   [N, Lq, M, L, P, 2]     (x, y) normalised to [0,1]; loc_dtype
+ *   attn_weight    [N, Lq, M, L, P]        loc_dtype
+ *   output / grad_output [N, Lq, M*D]      dtype
+ *   grad_value like value; grad_loc / grad_attn like sampling_loc / attn_weight.
+ *
+ * Thread safety: re-entrant.  The only process-wide state is the variant override (msda_select_variant, meant for
+ * profiling A/B runs) and one-time cudaFuncSetAttribute calls.  msda_last_error() is thread-local.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_VERSION 100 /* major*100 + minor */
+
+/* element types */
+#define MSDA_F32 0
+#define MSDA_BF16 1
+#define MSDA_F64 2
+
+/* status codes (< 0: argument errors; > 0: cudaError_t values) */
+#define MSDA_OK 0
+#define MSDA_ERR_NULL -1      /* a required pointer is NULL */
+#define MSDA_ERR_DIM -2       /* a dimension is <= 0 or overflows int32 indexing */
+#define MSDA_ERR_DTYPE -3     /* unsupported dtype / loc_dtype combination */
+#define MSDA_ERR_WORKSPACE -4 /* workspace too small (see msda_backward_workspace_bytes) */
+#define MSDA_ERR_VARIANT -5   /* unknown variant name, or the forced variant cannot run this shape */
+#define MSDA_ERR_STEP -6      /* N % min(N, im2col_step) != 0 (ms_deform_attn_cuda.cu:55-57) */
+
+/*
+ * Forward.  out[n,q,m*D+c] = sum_{l,p} attn * bilinear(value level l, loc*(W,H) - 0.5), zero outside the map
+ * (ms_deform_im2col_cuda.cuh:242-304, 38-89).
+ *
+ * shapes_host / level_start_host: optional host copies of the two int64 arrays (NULL if unknown).  With them the
+ * library can pick shape-specialised kernels (shared-memory slabs) without a device->host sync; without them
+ * only the kernels that read the geometry from device memory are used.  Contents must equal the device arrays.
+ * im2col_step: accepted for API compatibility; validated like the reference, otherwise unused (one launch
+ * covers the whole batch).
+ */
+int msda_forward(int dtype, int loc_dtype,
+                 const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const void *sampling_loc, const void *attn_weight, void *output,
+                 int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
+                 const int64_t *shapes_host, const int64_t *level_start_host,
+                 int device, void *stream);
+
+/*
+ * Backward (ms_deform_im2col_cuda.cuh:306-408, 92-164).  Writes all three gradients in full; the caller does
+ * not need to zero them.  workspace: device scratch of at least msda_backward_workspace_bytes(...) bytes
+ * (may be NULL when that is 0).
+ */
+int msda_backward(int dtype, int loc_dtype,
+                  const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                  const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                  void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
+                  int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
+                  const int64_t *shapes_host, const int64_t *level_start_host,
+                  void *workspace, size_t workspace_bytes,
+                  int device, void *stream);
+
+/* Scratch bytes msda_backward needs for this problem (0 for most float32 paths). */
+size_t msda_backward_workspace_bytes(int dtype, int loc_dtype, int N, int S, int M, int D, int L, int Lq, int P);
+
+/*
+ * Force a kernel variant for subsequent calls (profiling A/B runs): pass_ 0 = forward, 1 = backward;
+ * name = "auto" restores the default choice.  Returns MSDA_ERR_VARIANT for unknown names.
+ * msda_variant_name writes the variant the library would run (or last ran) for the pass.
+ */
+int msda_select_variant(int pass_, const char *name);
+const char *msda_variant_names(int pass_); /* comma-separated list */
+const char *msda_last_variant(int pass_);  /* name of the variant the calling thread last launched */
+
+/* Number of kernel launches (memsets excluded) issued by this library since load, for gpu_launches accounting. */
+uint64_t msda_launch_count(void);
+
+const char *msda_last_error(void); /* thread-local, never NULL */
+int msda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

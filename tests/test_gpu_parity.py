@@ -1,0 +1,306 @@
+"""GPU (-m gpu): parity of the sm_100a kernels, called through the C ABI, against the CPU oracle and the golden
+vectors generated from the reference.  Tolerances are north_star's: forward 1e-5 (fp32) / 1e-2 (bf16), gradients
+1e-4 (fp32), measured as max-norm relative error (conftest.rel_err)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import S4_SHAPES, level_start, load_golden, make_inputs, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = {torch.float32: 1e-5, torch.float64: 1e-12, torch.bfloat16: 1e-2}
+BWD_TOL = {torch.float32: 1e-4, torch.float64: 1e-11, torch.bfloat16: 2e-2}
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import combo_avs_b200
+    yield combo_avs_b200
+    combo_avs_b200.select_variant("forward", "auto")
+    combo_avs_b200.select_variant("backward", "auto")
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None and t.is_floating_point() else t
+
+
+def run_op(pkg, d, dtype=torch.float32, loc_dtype=None, step=128, backward=True, grad_out=None):
+    loc_dtype = loc_dtype or dtype
+    v = _dev(d["value"], dtype).requires_grad_(backward)
+    l = _dev(d["loc"], loc_dtype).requires_grad_(backward)
+    a = _dev(d["attn"], loc_dtype).requires_grad_(backward)
+    out = pkg.MSDeformAttnFunction.apply(v, _dev(d["shapes"]), _dev(d["start"]), l, a, step)
+    if not backward:
+        return out.detach().float().cpu().numpy() if dtype == torch.bfloat16 else out.detach().cpu().numpy()
+    go = _dev(grad_out if grad_out is not None else d.get("grad_out", np.ones(out.shape)), dtype)
+    out.backward(go)
+    torch.cuda.synchronize()
+    f = (lambda t: t.detach().float().cpu().numpy()) if dtype == torch.bfloat16 else (lambda t: t.detach().cpu().numpy())
+    return f(out), f(v.grad), f(l.grad), f(a.grad)
+
+
+def oracle_all(d, rounded_to=None, loc_rounded_to=None):
+    """fp64 oracle on the (optionally dtype-rounded) inputs the kernel actually sees."""
+    def rnd(x, dt):
+        if dt is None:
+            return np.asarray(x, dtype=np.float64)
+        return torch.from_numpy(np.asarray(x)).to(dt).double().numpy()
+    v = rnd(d["value"], rounded_to)
+    l, a = rnd(d["loc"], loc_rounded_to or rounded_to), rnd(d["attn"], loc_rounded_to or rounded_to)
+    out = oracle.forward(v, d["shapes"], d["start"], l, a)
+    go = rnd(d["grad_out"], rounded_to) if "grad_out" in d else np.ones_like(out)
+    return (out,) + tuple(oracle.backward(v, d["shapes"], d["start"], l, a, go))
+
+
+def variants(pkg, which):
+    return [v for v in pkg.variant_names(which) if v != "auto"]
+
+
+# ------------------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", ["testpy_fwd_double", "testpy_fwd_float", "testpy_grad_D30", "testpy_grad_D32",
+                                  "testpy_grad_D64", "testpy_grad_D71", "s4pyr_unit", "s4pyr_edge", "ragged_levels"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_golden_vectors(pkg, name, dtype):
+    g = load_golden(name)
+    pkg.select_variant("forward", "auto")
+    pkg.select_variant("backward", "auto")
+    out, gv, gl, ga = run_op(pkg, g, dtype, step=int(g["im2col_step"]))
+    assert out.shape == g["out"].shape
+    assert rel_err(out, g["out"]) < FWD_TOL[dtype]
+    assert rel_err(gv, g["grad_value"]) < BWD_TOL[dtype]
+    assert rel_err(gl, g["grad_loc"]) < BWD_TOL[dtype]
+    assert rel_err(ga, g["grad_attn"]) < BWD_TOL[dtype]
+
+
+def test_reference_testpy_tolerances(pkg):
+    """The reference's own acceptance checks (ops/test.py:49,67): allclose defaults in double, rtol 1e-2/atol 1e-3 in float."""
+    g = load_golden("testpy_fwd_double")
+    out = run_op(pkg, g, torch.float64, step=2, backward=False)
+    assert np.allclose(out, g["out"])
+    g = load_golden("testpy_fwd_float")
+    out = run_op(pkg, g, torch.float32, step=2, backward=False)
+    assert np.allclose(out, g["out_f32path"], rtol=1e-2, atol=1e-3)
+
+
+# --------------------------------------------------------------------------------- every variant, S4 production shape
+@pytest.mark.parametrize("N", [1, 5, 40])
+def test_s4_shape_all_variants_fp32(pkg, N):
+    d = make_inputs(N, S4_SHAPES, 8, 32, 1029, 4, seed=3 + N)
+    ref = oracle_all(d)
+    for fv in variants(pkg, "forward"):
+        pkg.select_variant("forward", fv)
+        out = run_op(pkg, d, backward=False)
+        assert pkg.last_variant("forward") == fv
+        assert rel_err(out, ref[0]) < 1e-5, fv
+    pkg.select_variant("forward", "auto")
+    for bv in variants(pkg, "backward"):
+        pkg.select_variant("backward", bv)
+        out, gv, gl, ga = run_op(pkg, d)
+        assert pkg.last_variant("backward") == bv
+        assert rel_err(gv, ref[1]) < 1e-4, bv
+        assert rel_err(gl, ref[2]) < 1e-4, bv
+        assert rel_err(ga, ref[3]) < 1e-4, bv
+    pkg.select_variant("backward", "auto")
+
+
+def test_s4_shape_edge_locations_all_variants(pkg):
+    """locations in [-0.3, 1.3]: out-of-range samples, footprints straddling every border."""
+    d = make_inputs(3, S4_SHAPES, 8, 32, 1029, 4, seed=11, lo=-0.3, hi=1.3)
+    ref = oracle_all(d)
+    for fv in variants(pkg, "forward"):
+        for bv in variants(pkg, "backward"):
+            pkg.select_variant("forward", fv)
+            pkg.select_variant("backward", bv)
+            out, gv, gl, ga = run_op(pkg, d)
+            assert rel_err(out, ref[0]) < 1e-5, fv
+            assert rel_err(gv, ref[1]) < 1e-4 and rel_err(gl, ref[2]) < 1e-4 and rel_err(ga, ref[3]) < 1e-4, bv
+    pkg.select_variant("forward", "auto")
+    pkg.select_variant("backward", "auto")
+
+
+def test_special_locations(pkg):
+    """exact borders, exact integers away from 0.5 (no floor ambiguity), NaN and huge coordinates."""
+    d = make_inputs(1, S4_SHAPES, 8, 32, 64, 4, seed=2)
+    loc = d["loc"]
+    loc[0, 0] = 0.0          # h = w = -0.5: half-outside top-left
+    loc[0, 1] = 1.0          # h = H - 0.5: half-outside bottom-right
+    loc[0, 2] = -1e30
+    loc[0, 3] = 1e30
+    loc[0, 4] = np.nan       # comparisons false -> skipped, as in the reference (cuh:294)
+    loc[0, 5, :, :, :, 0] = np.nan
+    loc[0, 6] = 0.25         # pixel coordinates x.25 / x.5 / x - exact in fp32
+    loc[0, 7] = -1.0 / 28.0  # around h = -1.5 ... outside
+    ref = oracle_all(d)
+    for fv in variants(pkg, "forward"):
+        for bv in variants(pkg, "backward"):
+            pkg.select_variant("forward", fv)
+            pkg.select_variant("backward", bv)
+            out, gv, gl, ga = run_op(pkg, d)
+            assert np.isfinite(out).all() and np.isfinite(gv).all() and np.isfinite(gl).all() and np.isfinite(ga).all()
+            assert rel_err(out, ref[0]) < 1e-5
+            assert rel_err(gv, ref[1]) < 1e-4 and rel_err(gl, ref[2]) < 1e-4 and rel_err(ga, ref[3]) < 1e-4
+            assert np.abs(out[0, 2:6]).max() == 0 and np.abs(gl[0, 2:6]).max() == 0 and np.abs(ga[0, 2:6]).max() == 0
+    pkg.select_variant("forward", "auto")
+    pkg.select_variant("backward", "auto")
+
+
+# ----------------------------------------------------------------------------------- generic widths, levels, dtypes
+@pytest.mark.parametrize("D", [1, 2, 4, 30, 32, 33, 64, 71, 128, 1025, 2048, 3096])
+def test_channel_widths_fp64(pkg, D):
+    """The widths the reference's gradcheck walks through (test.py:95) and a few more; one backward design covers all."""
+    d = make_inputs(1, [(6, 4), (3, 2)], 2, D, 2, 2, seed=D, dtype=np.float64)
+    ref = oracle_all(d)
+    out, gv, gl, ga = run_op(pkg, d, torch.float64, step=2)
+    assert rel_err(out, ref[0]) < 1e-12
+    assert rel_err(gv, ref[1]) < 1e-11 and rel_err(gl, ref[2]) < 1e-11 and rel_err(ga, ref[3]) < 1e-11
+
+
+@pytest.mark.parametrize("D", [30, 32, 64, 71])
+def test_gradcheck_like_reference(pkg, D):
+    """torch.autograd.gradcheck in double on all three differentiable inputs -- the reference's check_gradient_numerical
+    (test.py:74-88), same shapes, same seed convention."""
+    torch.manual_seed(3)
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
+    start = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    value = (torch.rand(N, S, M, D).cuda() * 0.01).double().requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2).cuda().double().requires_grad_(True)
+    attn = torch.rand(N, Lq, M, L, P).cuda() + 1e-5
+    attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
+    assert torch.autograd.gradcheck(pkg.MSDeformAttnFunction.apply, (value, shapes, start, loc, attn, 2))
+
+
+@pytest.mark.parametrize("shapes,M,D,Lq,P,N", [
+    ([(1, 1)], 1, 32, 1, 1, 1),
+    ([(5, 9), (3, 4), (2, 2), (1, 1)], 3, 8, 17, 3, 3),
+    ([(7, 7), (14, 14), (28, 28)], 8, 32, 100, 1, 2),     # P=1: lane groups span levels
+    ([(7, 7), (14, 14), (28, 28)], 8, 32, 33, 5, 2),      # L*P = 15, not a multiple of 4
+    ([(16, 16), (8, 8)], 4, 32, 300, 4, 7),
+    ([(2, 3)] * 9, 2, 32, 5, 2, 2),                       # 9 levels
+    ([(3, 3)] * 17, 1, 32, 4, 1, 1),                      # more levels than the D=32 kernels' table: generic path
+])
+def test_ragged_problem_shapes_fp32(pkg, shapes, M, D, Lq, P, N):
+    d = make_inputs(N, shapes, M, D, Lq, P, seed=len(shapes) * 7 + P, lo=-0.2, hi=1.2, normal=True)
+    ref = oracle_all(d)
+    pkg.select_variant("forward", "auto")
+    pkg.select_variant("backward", "auto")
+    out, gv, gl, ga = run_op(pkg, d, step=N)
+    assert rel_err(out, ref[0]) < 1e-5
+    assert rel_err(gv, ref[1]) < 1e-4 and rel_err(gl, ref[2]) < 1e-4 and rel_err(ga, ref[3]) < 1e-4
+
+
+def test_query_count_differs_from_value_length(pkg):
+    d = make_inputs(2, S4_SHAPES, 8, 32, 77, 4, seed=21)
+    ref = oracle_all(d)
+    out, gv, gl, ga = run_op(pkg, d)
+    assert out.shape == (2, 77, 256)
+    assert rel_err(out, ref[0]) < 1e-5 and rel_err(gv, ref[1]) < 1e-4
+
+
+@pytest.mark.parametrize("loc_dtype", [torch.float32, torch.bfloat16])
+def test_bf16(pkg, loc_dtype):
+    """bf16 has no counterpart in the reference (float/double dispatch only, ms_deform_attn_cuda.cu:69); its oracle is
+    the fp64 oracle on the bf16-rounded inputs. north_star: forward within 1e-2."""
+    d = make_inputs(4, S4_SHAPES, 8, 32, 1029, 4, seed=8)
+    ref = oracle_all(d, torch.bfloat16, loc_dtype)
+    out, gv, gl, ga = run_op(pkg, d, torch.bfloat16, loc_dtype)
+    assert rel_err(out, ref[0]) < 1e-2
+    assert rel_err(gv, ref[1]) < 2e-2 and rel_err(gl, ref[2]) < 2e-2 and rel_err(ga, ref[3]) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ empty and errors
+def test_empty_inputs(pkg):
+    shapes = torch.tensor(S4_SHAPES, device="cuda")
+    start = torch.tensor(level_start(S4_SHAPES), device="cuda")
+    out = pkg.ms_deform_attn_forward(torch.zeros(0, 1029, 8, 32, device="cuda"), shapes, start,
+                                     torch.zeros(0, 5, 8, 3, 4, 2, device="cuda"), torch.zeros(0, 5, 8, 3, 4, device="cuda"), 128)
+    assert out.shape == (0, 5, 256)
+    v = torch.rand(2, 1029, 8, 32, device="cuda")
+    out = pkg.ms_deform_attn_forward(v, shapes, start, torch.zeros(2, 0, 8, 3, 4, 2, device="cuda"),
+                                     torch.zeros(2, 0, 8, 3, 4, device="cuda"), 128)
+    assert out.shape == (2, 0, 256)
+    gv, gl, ga = pkg.ms_deform_attn_backward(v, shapes, start, torch.zeros(2, 0, 8, 3, 4, 2, device="cuda"),
+                                             torch.zeros(2, 0, 8, 3, 4, device="cuda"), torch.zeros(2, 0, 256, device="cuda"), 128)
+    assert gv.shape == v.shape and float(gv.abs().max()) == 0.0 and gl.numel() == 0 and ga.numel() == 0
+
+
+def test_im2col_step_rule_and_dtype_errors(pkg):
+    d = make_inputs(6, [(4, 4)], 2, 32, 3, 2)
+    args = [_dev(d[k]) for k in ("value", "shapes", "start", "loc", "attn")]
+    assert pkg.ms_deform_attn_forward(*args, 3).shape == (6, 3, 64)   # 6 % 3 == 0
+    assert pkg.ms_deform_attn_forward(*args, 128).shape == (6, 3, 64)  # min(6,128) = 6
+    with pytest.raises(RuntimeError, match="must divide"):            # 6 % 4 != 0 (ms_deform_attn_cuda.cu:57)
+        pkg.ms_deform_attn_forward(*args, 4)
+    with pytest.raises(RuntimeError, match="not implemented for 'float16'"):
+        pkg.ms_deform_attn_forward(args[0].half(), args[1], args[2], args[3].half(), args[4].half(), 6)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        pkg.ms_deform_attn_forward(args[0].transpose(0, 1), *args[1:], 6)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        pkg.ms_deform_attn_forward(args[0], args[1].cpu(), *args[2:], 6)
+
+
+# ------------------------------------------------------------------- size-independent properties at full S4 size (N=40, 80)
+@pytest.mark.parametrize("N", [40, 80])
+def test_full_size_properties(pkg, N):
+    d = make_inputs(N, S4_SHAPES, 8, 32, 1029, 4, seed=40)
+    for fv in variants(pkg, "forward"):
+        for bv in variants(pkg, "backward"):
+            if (fv == "generic") != (bv == "generic"):
+                continue
+            pkg.select_variant("forward", fv)
+            pkg.select_variant("backward", bv)
+            out, gv, gl, ga = run_op(pkg, d)
+            o64, g64 = out.astype(np.float64), d["grad_out"].astype(np.float64)
+            # adjoint identity: <out(v), g> == <v, grad_value(g)>  (the op is linear in value)
+            lhs, rhs = float((o64 * g64).sum()), float((d["value"].astype(np.float64) * gv).sum())
+            assert abs(lhs - rhs) < 1e-5 * abs(lhs), (fv, bv)
+            # sum_lp attn * grad_attn == <out, g> per (n, q, m)
+            per_qm = (d["attn"].astype(np.float64) * ga).sum(axis=(-1, -2))
+            ref = (o64 * g64).reshape(N, 1029, 8, 32).sum(-1)
+            assert rel_err(per_qm, ref) < 1e-5
+            # constant value field + in-range interior samples + normalised weights -> constant output
+            ones = dict(d, value=np.full_like(d["value"], 0.5), loc=(d["loc"] * 0.5 + 0.25))
+            out1 = run_op(pkg, ones, backward=False)
+            assert np.abs(out1 - 0.5).max() < 1e-5
+            # linearity: op(2v) == 2 op(v) bit-for-bit in fp32 (power-of-two scaling)
+            out2 = run_op(pkg, dict(d, value=d["value"] * 2), backward=False)
+            assert np.array_equal(out2, out * 2)
+    pkg.select_variant("forward", "auto")
+    pkg.select_variant("backward", "auto")
+
+
+def test_module_matches_reference_module(pkg):
+    """MSDeformAttn.forward against outputs of the reference module (CPU torch path) stored in the golden file:
+    2-d and 4-d reference points, with and without a padding mask."""
+    g = load_golden("module_small")
+    m = pkg.MSDeformAttn(d_model=32, n_levels=3, n_heads=2, n_points=4).double()
+    m.load_state_dict({k[3:].replace("__", "."): torch.from_numpy(v) for k, v in g.items() if k.startswith("sd_")})
+    m = m.cuda()
+    q, src = _dev(g["query"]), _dev(g["src"])
+    shapes, start = _dev(g["shapes"]), _dev(g["start"])
+    y2 = m(q, _dev(g["ref2"]), src, shapes, start, None)
+    y2m = m(q, _dev(g["ref2"]), src, shapes, start, _dev(g["mask"]))
+    y4 = m(q, _dev(g["ref4"]), src, shapes, start, None)
+    assert rel_err(y2.detach().cpu().numpy(), g["y2"]) < 1e-12
+    assert rel_err(y2m.detach().cpu().numpy(), g["y2_masked"]) < 1e-12
+    assert rel_err(y4.detach().cpu().numpy(), g["y4"]) < 1e-12
+    # fp32 module, gradients flow to every parameter and to the inputs
+    m32 = m.float()
+    q32 = q.float().requires_grad_(True)
+    y = m32(q32, _dev(g["ref2"]).float(), src.float(), shapes, start, None)
+    assert rel_err(y.detach().cpu().numpy(), g["y2"]) < 1e-4
+    y.square().mean().backward()
+    assert q32.grad is not None and all(p.grad is not None and torch.isfinite(p.grad).all() for p in m32.parameters())
+
+
+def test_non_default_stream_and_autograd_thread(pkg):
+    d = make_inputs(2, S4_SHAPES, 8, 32, 1029, 4, seed=6)
+    ref = oracle_all(d)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out, gv, gl, ga = run_op(pkg, d)
+    assert rel_err(out, ref[0]) < 1e-5 and rel_err(gv, ref[1]) < 1e-4

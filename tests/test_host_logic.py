@@ -1,0 +1,76 @@
+"""CPU: the host-side mirror of the reference interface (module, autograd function wrapper, error behaviour)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as g
+    g.build()
+    import combo_avs_b200
+    return combo_avs_b200
+
+
+def test_module_matches_reference_init(pkg):
+    g = load_golden("module_init_256")
+    torch.manual_seed(0)
+    m = pkg.MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4)
+    assert sum(p.numel() for p in m.parameters()) == int(g["n_params"]) == 205600
+    assert np.allclose(m.sampling_offsets.bias.detach().numpy(), g["offsets_bias"], atol=1e-6)  # ms_deform_attn.py:68-78
+    assert m.sampling_offsets.weight.abs().max() == 0
+    assert m.attention_weights.weight.abs().max() == 0 and m.attention_weights.bias.abs().max() == 0
+    assert m.value_proj.bias.abs().max() == 0 and m.output_proj.bias.abs().max() == 0
+    bound = float(g["value_weight_bound"])
+    assert 0.9 * bound < m.value_proj.weight.abs().max() <= bound + 1e-7  # xavier_uniform_
+    assert (m.im2col_step, m.d_model, m.n_levels, m.n_heads, m.n_points) == (128, 256, 3, 8, 4)
+
+
+def test_state_dict_is_reference_compatible(pkg):
+    g = load_golden("module_small")
+    m = pkg.MSDeformAttn(d_model=32, n_levels=3, n_heads=2, n_points=4).double()
+    ref_sd = {k[3:].replace("__", "."): torch.from_numpy(v) for k, v in g.items() if k.startswith("sd_")}
+    assert set(ref_sd) == set(m.state_dict())
+    m.load_state_dict(ref_sd, strict=True)
+
+
+def test_constructor_errors_and_warning(pkg):
+    with pytest.raises(ValueError):
+        pkg.MSDeformAttn(d_model=30, n_heads=8)
+    with pytest.warns(UserWarning):
+        pkg.MSDeformAttn(d_model=24, n_heads=2)  # head width 12: not a power of two
+
+
+def test_no_cpu_fallback(pkg):
+    """The reference module's bare except reroutes CPU tensors to the PyTorch path (ms_deform_attn.py:123-125);
+    the reference *extension* raises 'Not implemented on the CPU' (ms_deform_attn.h:43). We keep the latter."""
+    shapes = torch.tensor([[6, 4], [3, 2]])
+    start = torch.tensor([0, 24])
+    args = (torch.zeros(1, 30, 2, 2), shapes, start, torch.zeros(1, 2, 2, 2, 2, 2), torch.zeros(1, 2, 2, 2, 2), 2)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        pkg.MSDeformAttnFunction.apply(*args)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        pkg.ms_deform_attn_forward(*args)
+    m = pkg.MSDeformAttn(d_model=4, n_levels=2, n_heads=2, n_points=2)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 2, 4), torch.zeros(1, 2, 2, 2), torch.zeros(1, 30, 4), shapes, start)
+    with pytest.raises(ValueError, match="Last dim of reference_points"):
+        m(torch.zeros(1, 2, 4), torch.zeros(1, 2, 2, 3), torch.zeros(1, 30, 4), shapes, start)
+
+
+def test_contiguity_is_checked_like_the_reference(pkg):
+    shapes = torch.tensor([[6, 4], [3, 2]])
+    start = torch.tensor([0, 24])
+    value = torch.zeros(1, 30, 2, 4)[..., ::2]
+    with pytest.raises(RuntimeError, match="value tensor has to be contiguous"):
+        pkg.ms_deform_attn_forward(value, shapes, start, torch.zeros(1, 2, 2, 2, 2, 2), torch.zeros(1, 2, 2, 2, 2), 2)
+
+
+def test_missing_library_is_loud(pkg, monkeypatch, tmp_path):
+    from combo_avs_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libmsda_b200.so"))
+    with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
+        _lib.load()
