@@ -18,11 +18,11 @@ void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_r
 namespace {
 
 thread_local char t_error[512] = "";
-thread_local const char *t_last_variant[2] = {"none", "none"};
+std::atomic<const char *> g_last_variant[2] = {{"none"}, {"none"}};  // process-wide: backward runs on the autograd thread
 
-enum FwdVariant { kFwdAuto = 0, kFwdGeneric, kFwdWarp32, kFwdCount };
+enum FwdVariant { kFwdAuto = 0, kFwdGeneric, kFwdWarp32, kFwdSlab32, kFwdCount };
 enum BwdVariant { kBwdAuto = 0, kBwdGeneric, kBwdWarp32, kBwdCount };
-const char *const kFwdNames[kFwdCount] = {"auto", "generic", "warp32"};
+const char *const kFwdNames[kFwdCount] = {"auto", "generic", "warp32", "slab32"};
 const char *const kBwdNames[kBwdCount] = {"auto", "generic", "warp32"};
 std::atomic<int> g_forced[2] = {{0}, {0}};
 
@@ -153,10 +153,10 @@ uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_rela
 
 const char *msda_variant_names(int pass_)
 {
-    return pass_ == 0 ? "auto,generic,warp32" : "auto,generic,warp32";
+    return pass_ == 0 ? "auto,generic,warp32,slab32" : "auto,generic,warp32";
 }
 
-const char *msda_last_variant(int pass_) { return (pass_ == 0 || pass_ == 1) ? t_last_variant[pass_] : "none"; }
+const char *msda_last_variant(int pass_) { return (pass_ == 0 || pass_ == 1) ? g_last_variant[pass_].load() : "none"; }
 
 int msda_select_variant(int pass_, const char *name)
 {
@@ -188,9 +188,14 @@ int msda_forward(int dtype, int loc_dtype, const void *value, const int64_t *spa
     cudaStream_t st = (cudaStream_t)stream;
 
     int v = g_forced[0].load();
-    if (v == kFwdAuto) v = warp32_supported(p) ? kFwdWarp32 : kFwdGeneric;
+    if (v == kFwdAuto) v = slab32_supported(p) ? kFwdSlab32 : warp32_supported(p) ? kFwdWarp32 : kFwdGeneric;
     if (S == 0) v = kFwdGeneric;
     switch (v) {
+    case kFwdSlab32:
+        if (!slab32_supported(p))
+            return fail(MSDA_ERR_VARIANT, "forward variant slab32 needs f32, D=32, host geometry and a padded slab that fits shared memory");
+        e = fwd_slab32(p, output, st);
+        break;
     case kFwdWarp32:
         if (!warp32_supported(p)) return fail(MSDA_ERR_VARIANT, "forward variant warp32 needs f32, D=32, L<=%d", kMaxLevels);
         e = fwd_warp32(p, output, st);
@@ -200,7 +205,7 @@ int msda_forward(int dtype, int loc_dtype, const void *value, const int64_t *spa
         e = fwd_generic(p, output, st);
         break;
     }
-    t_last_variant[0] = kFwdNames[v];
+    g_last_variant[0].store(kFwdNames[v]);
     if (e != cudaSuccess) return cuda_fail(e, "msda_forward launch");
     return MSDA_OK;
 }
@@ -255,7 +260,7 @@ int msda_backward(int dtype, int loc_dtype, const void *value, const int64_t *sp
         e = bwd_generic(p, io, st);
         break;
     }
-    t_last_variant[1] = kBwdNames[v];
+    g_last_variant[1].store(kBwdNames[v]);
     if (e != cudaSuccess) return cuda_fail(e, "msda_backward launch");
     return MSDA_OK;
 }

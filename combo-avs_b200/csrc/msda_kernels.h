@@ -44,4 +44,8 @@ bool warp32_supported(const Problem &p);
 cudaError_t fwd_warp32(const Problem &p, void *out, cudaStream_t st);
 cudaError_t bwd_warp32(const Problem &p, const BackwardIO &io, cudaStream_t st);
 
+// slab32: D == 32, f32, host geometry: shared-memory slab gather (msda_slab32.cu)
+bool slab32_supported(const Problem &p);
+cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st);
+
 }  // namespace msda

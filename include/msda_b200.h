@@ -97,7 +97,7 @@ size_t msda_backward_workspace_bytes(int dtype, int loc_dtype, int N, int S, int
  */
 int msda_select_variant(int pass_, const char *name);
 const char *msda_variant_names(int pass_); /* comma-separated list */
-const char *msda_last_variant(int pass_);  /* name of the variant the calling thread last launched */
+const char *msda_last_variant(int pass_);  /* name of the variant last launched for the pass (process-wide) */
 
 /* Number of kernel launches (memsets excluded) issued by this library since load, for gpu_launches accounting. */
 uint64_t msda_launch_count(void);
