@@ -21,9 +21,9 @@ thread_local char t_error[512] = "";
 std::atomic<const char *> g_last_variant[2] = {{"none"}, {"none"}};  // process-wide: backward runs on the autograd thread
 
 enum FwdVariant { kFwdAuto = 0, kFwdGeneric, kFwdWarp32, kFwdSlab32, kFwdCount };
-enum BwdVariant { kBwdAuto = 0, kBwdGeneric, kBwdWarp32, kBwdCount };
+enum BwdVariant { kBwdAuto = 0, kBwdGeneric, kBwdWarp32, kBwdSorted32, kBwdCount };
 const char *const kFwdNames[kFwdCount] = {"auto", "generic", "warp32", "slab32"};
-const char *const kBwdNames[kBwdCount] = {"auto", "generic", "warp32"};
+const char *const kBwdNames[kBwdCount] = {"auto", "generic", "warp32", "sorted32"};
 std::atomic<int> g_forced[2] = {{0}, {0}};
 
 int fail(int code, const char *fmt, ...)
@@ -153,7 +153,7 @@ uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_rela
 
 const char *msda_variant_names(int pass_)
 {
-    return pass_ == 0 ? "auto,generic,warp32,slab32" : "auto,generic,warp32";
+    return pass_ == 0 ? "auto,generic,warp32,slab32" : "auto,generic,warp32,sorted32";
 }
 
 const char *msda_last_variant(int pass_) { return (pass_ == 0 || pass_ == 1) ? g_last_variant[pass_].load() : "none"; }
@@ -248,9 +248,14 @@ int msda_backward(int dtype, int loc_dtype, const void *value, const int64_t *sp
 
     BackwardIO io{grad_output, grad_value, grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes};
     int v = g_forced[1].load();
-    if (v == kBwdAuto) v = warp32_supported(p) ? kBwdWarp32 : kBwdGeneric;
+    if (v == kBwdAuto) v = sorted32_supported(p) ? kBwdSorted32 : warp32_supported(p) ? kBwdWarp32 : kBwdGeneric;
     if (S == 0) v = kBwdGeneric;
     switch (v) {
+    case kBwdSorted32:
+        if (!sorted32_supported(p))
+            return fail(MSDA_ERR_VARIANT, "backward variant sorted32 needs f32, D=32, host geometry, Lq*P <= 4608, (H+1)*(W+1) <= 1024 per level");
+        e = bwd_sorted32(p, io, st);
+        break;
     case kBwdWarp32:
         if (!warp32_supported(p)) return fail(MSDA_ERR_VARIANT, "backward variant warp32 needs f32, D=32, L<=%d", kMaxLevels);
         e = bwd_warp32(p, io, st);

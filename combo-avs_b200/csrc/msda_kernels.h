@@ -48,4 +48,8 @@ cudaError_t bwd_warp32(const Problem &p, const BackwardIO &io, cudaStream_t st);
 bool slab32_supported(const Problem &p);
 cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st);
 
+// sorted32: D == 32, f32, host geometry: sort-and-segment backward (msda_sorted32.cu)
+bool sorted32_supported(const Problem &p);
+cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st);
+
 }  // namespace msda

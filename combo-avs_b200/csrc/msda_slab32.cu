@@ -66,13 +66,44 @@ __device__ __forceinline__ void load_slab(float4 *slab, const float *__restrict_
     cp_async_wait_all();
 }
 
-template <int P_T>
+// floor for |x| < 2^22 without the XU pipe: adding 1.5*2^23 with round-down leaves floor(x) in the low mantissa bits
+__device__ __forceinline__ void floor_split(float x, float &fl, int &i)
+{
+    const float t = __fadd_rd(x, 12582912.f);
+    fl = t - 12582912.f;
+    i = __float_as_int(t) - 0x4B400000;
+}
+
+// Stage the sampling locations + attention weights of one pass (queries [q0, q0+cnt) of slab nm) into shared memory:
+// per query 2*LP location floats followed by LP weights (row of 3*LP floats).  In global memory one (query, head)
+// owns 8*LP contiguous bytes of locations and 4*LP of weights at a stride of M times that, so 16-byte cp.async
+// pieces issued by consecutive lanes touch each 128-byte line once, instead of once per sample per query.
+__device__ __forceinline__ void stage_meta(float *meta, const float *__restrict__ loc, const float *__restrict__ attn,
+                                           const SlabParams &sp, int LP, long long nm, int q0, int cnt)
+{
+    const long long n = nm / sp.M;
+    const int m = (int)(nm - n * sp.M);
+    const int pieces = (3 * LP) >> 2, loc_pieces = LP >> 1;
+    const int total = cnt * pieces;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int ql = i / pieces, pc = i - ql * pieces;
+        const long long qm = (n * sp.Lq + q0 + ql) * sp.M + m;
+        const float *src = pc < loc_pieces ? loc + qm * (2 * LP) + pc * 4 : attn + qm * LP + (pc - loc_pieces) * 4;
+        cp_async16(meta + ql * (3 * LP) + pc * 4, src);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int P_T, bool STAGE>
 __global__ void __launch_bounds__(512, 1)
 fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc, const float *__restrict__ attn,
                   float *__restrict__ out, const __grid_constant__ SlabParams sp)
 {
     extern __shared__ float4 slab[];
     const int P = P_T > 0 ? P_T : sp.P;
+    const int LP = sp.L * P;
+    float *meta0 = reinterpret_cast<float *>(slab + (size_t)sp.padded_rows * 8);  // two staging buffers of qpp rows
+    const int meta_stride = sp.qpp * 3 * LP;
     for (int i = threadIdx.x; i < sp.padded_rows * 8; i += blockDim.x) slab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long u_lo = sp.units * blockIdx.x / gridDim.x, u_hi = sp.units * (blockIdx.x + 1) / gridDim.x;
     const int pair = threadIdx.x >> 1, half = threadIdx.x & 1;
@@ -80,24 +111,41 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
 #pragma unroll
     for (int k = 0; k < 4; ++k) off[k] = (half * 4 + ((k + pair) & 3)) * 16;
     const unsigned slab_s = (unsigned)__cvta_generic_to_shared(slab);
-    const int LP = sp.L * P;
     long long resident = -1;
+    auto pass_range = [&](long long u, long long &nm, int &q0, int &cnt) {
+        nm = u / sp.pps;
+        q0 = (int)(u - nm * sp.pps) * sp.qpp;
+        cnt = min(sp.qpp, sp.Lq - q0);
+        if (cnt < 0) cnt = 0;
+    };
+    if (STAGE && u_lo < u_hi) {
+        long long nm; int q0, cnt;
+        pass_range(u_lo, nm, q0, cnt);
+        stage_meta(meta0, loc, attn, sp, LP, nm, q0, cnt);
+    }
     for (long long u = u_lo; u < u_hi; ++u) {
-        const long long nm = u / sp.pps;
-        const int pass = (int)(u - nm * sp.pps);
+        long long nm; int q0, cnt;
+        pass_range(u, nm, q0, cnt);
+        const float *meta = meta0 + ((u - u_lo) & 1) * meta_stride;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // staged metadata visible; everyone is done with the previous pass (and the zero fill)
         if (nm != resident) {
-            __syncthreads();  // everyone finished with the previous slab (and with the zero fill)
             load_slab(slab, value, sp, nm);
             __syncthreads();
             resident = nm;
         }
-        const int q = pass * sp.qpp + pair;
-        if (pair >= sp.qpp || q >= sp.Lq) continue;
+        if (STAGE && u + 1 < u_hi) {  // prefetch the next pass's metadata while this one computes
+            long long nm2; int q02, cnt2;
+            pass_range(u + 1, nm2, q02, cnt2);
+            stage_meta(meta0 + ((u + 1 - u_lo) & 1) * meta_stride, loc, attn, sp, LP, nm2, q02, cnt2);
+        }
+        if (pair >= cnt) continue;
+        const int q = q0 + pair;
         const long long n = nm / sp.M;
         const int m = (int)(nm - n * sp.M);
         const long long qm = (n * sp.Lq + q) * sp.M + m;
-        const float2 *loc2 = reinterpret_cast<const float2 *>(loc) + qm * LP;
-        const float *att = attn + qm * LP;
+        const float2 *loc2 = STAGE ? reinterpret_cast<const float2 *>(meta + pair * 3 * LP) : reinterpret_cast<const float2 *>(loc) + qm * LP;
+        const float *att = STAGE ? meta + pair * 3 * LP + 2 * LP : attn + qm * LP;
         float4 acc[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -108,20 +156,23 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
             const unsigned lvl_s = slab_s + (unsigned)(sp.prow0[l] + pitch + 1) * kRowBytes;  // address of pixel (0,0)
             const unsigned pitch_b = (unsigned)pitch * kRowBytes;
 #pragma unroll
-            for (int p = 0; p < (P_T > 0 ? P_T : 1); ++p) {
-                for (int pp = (P_T > 0 ? p : 0); pp < (P_T > 0 ? p + 1 : P); ++pp) {
-                    const int s = l * P + pp;
-                    const float2 xy = __ldg(loc2 + s);
-                    float a = __ldg(att + s);
+            for (int pp = 0; pp < (P_T > 0 ? P_T : 1); ++pp) {
+                for (int p = (P_T > 0 ? pp : 0); p < (P_T > 0 ? pp + 1 : P); ++p) {
+                    const int s = l * P + p;
+                    const float2 xy = STAGE ? loc2[s] : __ldg(loc2 + s);
+                    float a = STAGE ? att[s] : __ldg(att + s);
                     const float h = __fmaf_rn(xy.y, Hf, -0.5f), w = __fmaf_rn(xy.x, Wf, -0.5f);
                     const bool ok = h > -1.f && w > -1.f && h < Hf && w < Wf;
                     a = ok ? a : 0.f;
                     const float hc = fminf(fmaxf(h, -1.f), hmax), wc = fminf(fmaxf(w, -1.f), wmax);
-                    const float fh = floorf(hc), fw = floorf(wc);
+                    float fh, fw;
+                    int y0, x0;
+                    floor_split(hc, fh, y0);
+                    floor_split(wc, fw, x0);
                     const float lh = hc - fh, lw = wc - fw;
                     const float ahh = a * (1.f - lh), alh = a * lh, hw = 1.f - lw;
                     const float w1 = ahh * hw, w2 = ahh * lw, w3 = alh * hw, w4 = alh * lw;
-                    const unsigned r00 = lvl_s + (unsigned)((int)fh * pitch + (int)fw) * kRowBytes;
+                    const unsigned r00 = lvl_s + (unsigned)(y0 * pitch + x0) * kRowBytes;
                     const unsigned r10 = r00 + pitch_b;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -142,6 +193,7 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
 #pragma unroll
         for (int k = 0; k < 4; ++k) *reinterpret_cast<float4 *>(o + (off[k] >> 2)) = acc[k];
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // choose passes-per-slab so that N*M*pps units spread evenly over `ctas` persistent CTAs
@@ -164,7 +216,7 @@ void plan_passes(int Lq, long long slabs, int ctas, int max_pairs, int &qpp, int
     }
 }
 
-bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &threads, int &grid)
+bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &threads, int &grid, bool &stage)
 {
     if (!(p.dtype == 0 && p.loc_dtype == 0 && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
     sp.L = p.L; sp.P = p.P; sp.S = p.S; sp.M = p.M; sp.Lq = p.Lq;
@@ -181,7 +233,7 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
     }
     sp.padded_rows = rows;
     smem_bytes = (size_t)rows * kRowBytes;
-    if (smem_bytes > (size_t)p.smem_optin) return false;
+    if (smem_bytes + 4096 > (size_t)p.smem_optin) return false;
     const long long slabs = (long long)p.N * p.M;
     grid = (int)(slabs * 16 < p.sm_count ? slabs * 16 : p.sm_count);
     if (grid < 1) grid = 1;
@@ -189,6 +241,11 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
     sp.units = slabs * sp.pps;
     threads = ((sp.qpp * 2 + 31) / 32) * 32;
     if (threads > 512) threads = 512;
+    // metadata staging (two buffers of qpp rows of 3*L*P floats) when 16-byte pieces line up and it fits
+    const int LP = p.L * p.P;
+    const size_t meta_bytes = 2 * (size_t)sp.qpp * 3 * LP * sizeof(float);
+    stage = (LP % 4 == 0) && smem_bytes + meta_bytes <= (size_t)p.smem_optin;
+    if (stage) smem_bytes += meta_bytes;
     return true;
 }
 
@@ -199,7 +256,8 @@ bool slab32_supported(const Problem &p)
     SlabParams sp;
     size_t smem;
     int threads, grid;
-    return make_params(p, sp, smem, threads, grid);
+    bool stage;
+    return make_params(p, sp, smem, threads, grid, stage);
 }
 
 cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st)
@@ -207,9 +265,11 @@ cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st)
     SlabParams sp;
     size_t smem;
     int threads, grid;
-    if (!make_params(p, sp, smem, threads, grid)) return cudaErrorInvalidValue;
+    bool stage;
+    if (!make_params(p, sp, smem, threads, grid, stage)) return cudaErrorInvalidValue;
     if ((long long)p.N * p.M * p.Lq == 0) return cudaSuccess;
-    auto kern = p.P == 4 ? fwd_slab32_kernel<4> : fwd_slab32_kernel<0>;
+    auto kern = p.P == 4 ? (stage ? fwd_slab32_kernel<4, true> : fwd_slab32_kernel<4, false>)
+                         : (stage ? fwd_slab32_kernel<0, true> : fwd_slab32_kernel<0, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, threads, smem, st>>>((const float *)p.value, (const float *)p.loc, (const float *)p.attn, (float *)out, sp);
