@@ -196,6 +196,7 @@ def run_ours(args):
 
     import combo_avs_b200 as pkg
     from combo_avs_b200.host_api import HostPipeline
+    from combo_avs_b200.sharding import max_over_ranks
 
     if args.fwd_variant:
         pkg.select_variant("forward", args.fwd_variant)
@@ -231,11 +232,7 @@ def run_ours(args):
             fn(i)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = max_over_ranks(e0.elapsed_time(e1), dev)
         return ms, (t0, time.time())
 
     uuid = None
@@ -296,10 +293,7 @@ def run_ours(args):
     barrier()
     t1 = time.time()
     e2e_s = (t1 - t0) / e2e_steps  # host wall clock: the call returns only when results are on the host
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(e2e_s, dev)
     windows.append((t0, t1))
     e2e = {"value": world * nF / e2e_s, "unit": UNIT, "h2d_bytes_per_step": xfer["h2d"], "d2h_bytes_per_step": xfer["d2h"],
            "ms_per_step": e2e_s * 1e3, "api": "combo_avs_b200.host_api.HostPipeline.forward_backward (pinned host tensors, %d-frame chunks, 3 streams)" % args.e2e_chunk}

@@ -74,3 +74,32 @@ def test_missing_library_is_loud(pkg, monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libmsda_b200.so"))
     with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
         _lib.load()
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_reference_python_files_bind_to_the_shim(pkg):
+    """The reference's own ms_deform_attn_func.py, unmodified, resolves `import MultiScaleDeformableAttention` to the shim and
+    reaches libmsda_b200 through it (here on CPU it must hit the extension's 'Not implemented on the CPU' error, not a
+    PyTorch fallback)."""
+    import importlib
+    import os
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "combo-avs_b200", "shim")
+    ref = "/root/reference/models/modeling/pixel_decoder"
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "MultiScaleDeformableAttention" or k == "ops" or k.startswith("ops.")}
+    sys.path[:0] = [shim, ref]
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            mod = importlib.import_module("ops.functions.ms_deform_attn_func")
+        assert mod.MSDA.ms_deform_attn_forward is pkg.ms_deform_attn_forward
+        shapes, start = torch.tensor([[6, 4], [3, 2]]), torch.tensor([0, 24])
+        with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+            mod.MSDeformAttnFunction.apply(torch.zeros(1, 30, 2, 2), shapes, start, torch.zeros(1, 2, 2, 2, 2, 2), torch.zeros(1, 2, 2, 2, 2), 2)
+    finally:
+        sys.path.remove(shim)
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k == "MultiScaleDeformableAttention" or k == "ops" or k.startswith("ops.")]:
+            sys.modules.pop(k)
+        sys.modules.update(saved)
