@@ -10,10 +10,11 @@
 //   - the four value rows of the current cell live in registers (loaded once per cell, not once per sample),
 //   - grad_value for the four rows accumulates in registers and leaves with ONE vector reduction per row per cell
 //     visit (about 1.5 M row reductions instead of 15.8 M),
-//   - per sample only ONE 128-byte row is read: its grad_output row, from a shared-memory slab of grad_out[n,:,m,:],
+//   - per sample only ONE 128-byte row is read: its grad_output row, streamed from L2 and prefetched one sample ahead
+//     (the value level slab, zero-padded, sits in shared memory so a cell switch costs 8 LDS, not 8 L2 round trips),
 //   - grad_sampling_loc / grad_attn_weight are 4-lane shuffle reductions and plain stores.
-// A lane group is 4 lanes x 8 channels; group parity picks which of its two 16-byte chunks a lane loads first, so
-// the 8 lanes of every LDS.128 phase cover all 32 banks: conflict-free random row reads.
+// A lane group is 8 lanes x 4 channels (one 128-byte row per LDS.128 phase: conflict-free); the three per-sample sums
+// are reduced over the 8 lanes with a transposed butterfly (4 shuffles instead of 9).
 #include <cmath>
 
 #include "msda_kernels.h"
@@ -22,16 +23,18 @@ namespace msda {
 namespace {
 
 constexpr int kD = 32;
-constexpr int kThreads = 512;
-constexpr int kGroups = kThreads / 4;
-constexpr int kRounds = 9;          // samples per thread held in registers between the count and the fill pass
-constexpr int kMaxCells = 1024;     // (H+1)*(W+1) per level, scanned by 512 threads x 2
-constexpr int kInvalid = 0xfff;
+constexpr int kThreads = 768;
+constexpr int kGroups = kThreads / 8;
+constexpr int kRounds = 6;          // samples per thread held in registers between the count and the fill pass
+constexpr int kMaxCells = 1024;     // cell-grid size per level, scanned two per thread
 
 struct SortParams {
     int L, P, S, M, Lq;
     int H[kMaxLevels], W[kMaxLevels], start[kMaxLevels];
-    long long units;  // N*M*L
+    int cshift[kMaxLevels];  // log2 of the cell-grid pitch (power of two >= W+1): cell = (y0+1) << cshift | (x0+1)
+    unsigned wrecip[kMaxLevels];  // ceil(2^32 / W): pixel / W == umulhi(pixel, wrecip) for pixel < 2^16
+    int vrows_max;           // rows of the largest zero-padded level slab, (H+2)*(W+2)
+    long long units;         // N*M*L
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
@@ -40,74 +43,112 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 
-__device__ __forceinline__ float4 lds4(unsigned addr)
+
+// packed fp32x2 helpers (FFMA2 / FADD2 on sm_100a): halve the issue slots of the per-channel math
+struct f4p {
+    float2 lo, hi;
+};
+__device__ __forceinline__ f4p pk(float4 v) { return {make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
+__device__ __forceinline__ f4p psub(f4p a, f4p b)
 {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
+    const float2 m1 = make_float2(-1.f, -1.f);
+    return {__ffma2_rn(b.lo, m1, a.lo), __ffma2_rn(b.hi, m1, a.hi)};
+}
+__device__ __forceinline__ float floor_magic(float x, int &i)
+{
+    const float t = __fadd_rd(x, 12582912.f);  // valid for |x| < 2^22
+    i = __float_as_int(t) - 0x4B400000;
+    return t - 12582912.f;
 }
 
-__device__ __forceinline__ float4 f4sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
-
+template <int P_T>
 __global__ void __launch_bounds__(kThreads, 1)
 bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ loc, const float *__restrict__ attn,
                     const float *__restrict__ grad_out, float *__restrict__ grad_value, float *__restrict__ grad_loc,
                     float *__restrict__ grad_attn, const __grid_constant__ SortParams sp)
 {
     extern __shared__ float4 smem4[];
-    const int Lq = sp.Lq, P = sp.P, EP = Lq * P, LP = sp.L * P;
-    float4 *G4 = smem4;                       // grad_out[n, :, m, :]  -> Lq rows of 8 float4
-    float4 *ent = smem4 + (size_t)Lq * 8;     // sorted samples: {lh, lw, attn, cell<<20 | p<<16 | q}; later their results
-    int *cell_off = reinterpret_cast<int *>(ent + EP);   // kMaxCells + 1 counters -> exclusive offsets
+    const int Lq = sp.Lq, P = P_T > 0 ? P_T : sp.P, EP = Lq * P, LP = sp.L * P;
+    float4 *V4 = smem4;                                   // zero-padded value slab of the current level: (H+2) x (W+2) rows
+    float4 *ent = smem4 + (size_t)sp.vrows_max * 8;       // sorted samples: {lh, lw, attn, cell<<20 | p<<16 | q}
+    int *cell_off = reinterpret_cast<int *>(ent + EP);    // kMaxCells + 1 counters -> exclusive offsets
     int *warp_tot = cell_off + kMaxCells + 8;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int grp = tid >> 2, sub = tid & 3, par = grp & 1;
-    const int c0 = 2 * sub + par, c1 = 2 * sub + 1 - par;  // the two 16-byte chunks of a row this lane owns (load order)
-    const unsigned G_s = (unsigned)__cvta_generic_to_shared(G4);
+    const int grp = tid >> 3, j = tid & 7;                // 8 lanes per sample, lane j owns channels [4j, 4j+4)
     const int pix = sp.M * kD;
+    const int qstride = sp.M * LP;  // samples between consecutive queries of one head
 
     const long long u_lo = sp.units * blockIdx.x / gridDim.x, u_hi = sp.units * (blockIdx.x + 1) / gridDim.x;
-    long long resident = -1;
     for (long long u = u_lo; u < u_hi; ++u) {
         const long long nm = u / sp.L;
         const int l = (int)(u - nm * sp.L);
         const long long n = nm / sp.M;
         const int m = (int)(nm - n * sp.M);
-        const int H = sp.H[l], W = sp.W[l], CW = W + 1, cells = (H + 1) * CW;
+        const int H = sp.H[l], W = sp.W[l], cs = sp.cshift[l], cells = (H + 1) << cs, Wp = W + 2;
         const float Hf = (float)H, Wf = (float)W;
-        __syncthreads();  // previous unit is completely finished with ent / cell_off (and G if the slab changes)
-        if (nm != resident) {
-            const float *src = grad_out + (n * Lq * sp.M + m) * kD;
-            for (int i = tid; i < Lq * 8; i += kThreads) cp_async16(G4 + i, src + (long long)(i >> 3) * pix + (i & 7) * 4);
-            resident = nm;
+        const long long lvl_row = (n * sp.S + sp.start[l]) * (long long)pix + (long long)m * kD;  // pixel (0,0), channel 0
+        const float *vbase = value + lvl_row;
+        __syncthreads();  // previous unit is completely finished with V / ent / cell_off
+        // value level slab -> shared memory (interior by cp.async, the one-pixel border zeroed by hand)
+        for (int i = tid; i < H * W * 8; i += kThreads) {
+            const int pxl = i >> 3, c = i & 7;
+            const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
+            cp_async16(V4 + ((y + 1) * Wp + x + 1) * 8 + c, vbase + pxl * pix + c * 4);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < Wp * 8; i += kThreads) {  // top and bottom padded rows
+                V4[i] = z;
+                V4[(H + 1) * Wp * 8 + i] = z;
+            }
+            for (int i = tid; i < H * 16; i += kThreads) {  // left and right padded columns
+                const int y = (i >> 4) + 1, side = (i >> 3) & 1, c = i & 7;
+                V4[(y * Wp + side * (W + 1)) * 8 + c] = z;
+            }
+        }
         for (int i = tid; i <= cells; i += kThreads) cell_off[i] = 0;
-        __syncthreads();
 
         // ---- pass 1: cell of every sample of this level, rank inside the cell (shared-memory integer atomics) ----------
+        // sample (q, p) of this (n, m, l) sits at loc2[q*qstride + p]; per-unit base pointers keep the index math 32-bit
+        const long long meta0 = ((n * Lq) * sp.M + m) * (long long)LP + l * P;
+        const float2 *loc2 = reinterpret_cast<const float2 *>(loc) + meta0;
+        const float *att = attn + meta0;
+        float *gloc = grad_loc + 2 * meta0;
+        float *gatt = grad_attn + meta0;
         float sx[kRounds], sy[kRounds], sa[kRounds];
         int cr[kRounds];  // cell << 16 | rank, or -1
-        const long long meta0 = ((n * Lq) * sp.M + m) * (long long)LP + l * P;  // sample (q=0, p=0) of this (n, m, l)
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {  // all loads first: one L2 round trip for the whole pass
+            const int i = tid + r * kThreads;
+            sx[r] = sy[r] = 2.f;  // out of range
+            sa[r] = 0.f;
+            if (i < EP) {
+                const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
+                const float2 xy = __ldg(loc2 + q * qstride + p);
+                sx[r] = xy.x;
+                sy[r] = xy.y;
+                sa[r] = __ldg(att + q * qstride + p);
+            }
+        }
+        __syncthreads();  // counters are zero
 #pragma unroll
         for (int r = 0; r < kRounds; ++r) {
             const int i = tid + r * kThreads;
             cr[r] = -1;
-            sx[r] = sy[r] = sa[r] = 0.f;
             if (i < EP) {
-                const int q = i / P, p = i - q * P;
-                const long long s = meta0 + (long long)q * sp.M * LP + p;
-                const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + s);
-                sx[r] = xy.x;
-                sy[r] = xy.y;
-                sa[r] = __ldg(attn + s);
-                const float h = __fmaf_rn(xy.y, Hf, -0.5f), w = __fmaf_rn(xy.x, Wf, -0.5f);
+                const float h = __fmaf_rn(sy[r], Hf, -0.5f), w = __fmaf_rn(sx[r], Wf, -0.5f);
                 if (h > -1.f && w > -1.f && h < Hf && w < Wf) {
-                    const int cell = ((int)floorf(h) + 1) * CW + (int)floorf(w) + 1;
+                    int y0, x0;
+                    floor_magic(h, y0);
+                    floor_magic(w, x0);
+                    const int cell = ((y0 + 1) << cs) + x0 + 1;
                     cr[r] = (cell << 16) | atomicAdd(&cell_off[cell], 1);
                 } else {  // sample outside the map: all three gradients are exactly zero (cuh:352-356)
-                    *reinterpret_cast<float2 *>(grad_loc + 2 * s) = make_float2(0.f, 0.f);
-                    grad_attn[s] = 0.f;
+                    const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
+                    const int s = q * qstride + p;
+                    *reinterpret_cast<float2 *>(gloc + 2 * s) = make_float2(0.f, 0.f);
+                    gatt[s] = 0.f;
                 }
             }
         }
@@ -147,113 +188,124 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         for (int r = 0; r < kRounds; ++r) {
             if (cr[r] >= 0) {
                 const int i = tid + r * kThreads;
-                const int q = i / P, p = i - q * P;
+                const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
                 const int cell = cr[r] >> 16, rank = cr[r] & 0xffff;
                 const float h = __fmaf_rn(sy[r], Hf, -0.5f), w = __fmaf_rn(sx[r], Wf, -0.5f);
-                const float lh = h - floorf(h), lw = w - floorf(w);
+                int dummy;
+                const float lh = h - floor_magic(h, dummy), lw = w - floor_magic(w, dummy);
                 ent[cell_off[cell] + rank] = make_float4(lh, lw, sa[r], __int_as_float((cell << 20) | (p << 16) | q));
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();  // sorted list complete, grad_out slab landed
+        __syncthreads();  // sorted list complete, value slab landed
 
-        // ---- walk the sorted list: every 4-lane group owns a contiguous range of entries -----------------------------------
+        // ---- walk the sorted list: every 8-lane group owns a contiguous range of entries -----------------------------------
         const int E = cell_off[kMaxCells];
         const int e_lo = (int)((long long)E * grp / kGroups), e_hi = (int)((long long)E * (grp + 1) / kGroups);
         const int iters = (E + kGroups - 1) / kGroups;
-        const long long lvl_row = (n * sp.S + sp.start[l]) * (long long)pix + (long long)m * kD;  // element offset of pixel (0,0), channel 0
-        const long long out0 = ((n * Lq) * sp.M + m) * (long long)LP + l * P;
-        int cur = -1;
-        long long rowoff = 0;                 // element offset of the current cell's top-left neighbour (may be outside the map)
-        bool in00 = false, in01 = false, in10 = false, in11 = false;
-        float4 v00[2], dW[2], dH[2], dd[2];   // per owned chunk: V00, V01-V00, V10-V00, V11-V10-V01+V00
-        float4 a00[2], a01[2], a10[2], a11[2];  // grad_value accumulators of the four neighbour rows
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < 2; ++k) a00[k] = a01[k] = a10[k] = a11[k] = z4;
+        // grad_out row of query q, this lane's chunk: gobase + q*pix; streamed from L2, prefetched one entry ahead
+        const float *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD + j * 4;
+        float *gbase = grad_value + lvl_row + j * 4;
+        const int o01 = pix, o10 = W * pix, o11 = (W + 1) * pix;
+        const float4 *Vj = V4 + j;            // this lane's 16-byte chunk of padded row r is Vj[r*8]
+        // lanes 0..2 of a group store the three per-sample results: lane 0 grad_attn, lane 1 grad_loc.y, lane 2 grad_loc.x
+        float *res_base = j == 0 ? gatt : gloc + (j == 1 ? 1 : 0);
+        const int res_stride = j == 0 ? 1 : 2;
+        const float res_scale = j == 0 ? 1.f : (j == 1 ? Hf : Wf);
+        int cur = -1, inmask = 0;
+        float *gp = gbase;         // grad_value row of the current cell's top-left neighbour (this lane's chunk)
+        f4p v00, dW, dH, dd;       // V00, V01-V00, V10-V00, V11-V10-V01+V00 (this lane's 4 channels)
+        f4p a00, a01, a10, a11;    // grad_value accumulators of the four neighbour rows
+        const float2 z2 = make_float2(0.f, 0.f);
+        a00 = a01 = a10 = a11 = {z2, z2};
 
-        auto flush = [&]() {
-            if (cur < 0) return;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int ch = (k == 0 ? c0 : c1) * 4;
-                if (in00) red_add_v4(grad_value + rowoff + ch, a00[k].x, a00[k].y, a00[k].z, a00[k].w);
-                if (in01) red_add_v4(grad_value + rowoff + pix + ch, a01[k].x, a01[k].y, a01[k].z, a01[k].w);
-                if (in10) red_add_v4(grad_value + rowoff + (long long)W * pix + ch, a10[k].x, a10[k].y, a10[k].z, a10[k].w);
-                if (in11) red_add_v4(grad_value + rowoff + (long long)(W + 1) * pix + ch, a11[k].x, a11[k].y, a11[k].z, a11[k].w);
-                a00[k] = a01[k] = a10[k] = a11[k] = z4;
-            }
-        };
-
-        for (int it = 0; it < iters; ++it) {
-            const int e = e_lo + it;
-            const bool active = e < e_hi;
-            float s_a = 0.f, s_h = 0.f, s_w = 0.f;
-            int q = 0, p = 0;
-            float att = 0.f;
-            if (active) {
-                const float4 en = ent[e];
-                const int packed = __float_as_int(en.w);
-                const int cell = packed >> 20;
-                q = packed & 0xffff;
-                p = (packed >> 16) & 0xf;
-                att = en.z;
-                if (cell != cur) {
-                    flush();
-                    cur = cell;
-                    const int cy = cell / CW, y0 = cy - 1, x0 = cell - cy * CW - 1;
-                    const bool top = y0 >= 0, bot = y0 + 1 <= H - 1, lef = x0 >= 0, rig = x0 + 1 <= W - 1;
-                    in00 = top && lef; in01 = top && rig; in10 = bot && lef; in11 = bot && rig;
-                    rowoff = lvl_row + (long long)(y0 * W + x0) * pix;
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int ch = (k == 0 ? c0 : c1) * 4;
-                        const float4 t00 = in00 ? ldg4(value + rowoff + ch) : z4;
-                        const float4 t01 = in01 ? ldg4(value + rowoff + pix + ch) : z4;
-                        const float4 t10 = in10 ? ldg4(value + rowoff + (long long)W * pix + ch) : z4;
-                        const float4 t11 = in11 ? ldg4(value + rowoff + (long long)(W + 1) * pix + ch) : z4;
-                        v00[k] = t00;
-                        dW[k] = f4sub(t01, t00);
-                        dH[k] = f4sub(t10, t00);
-                        dd[k] = f4sub(f4sub(t11, t10), dW[k]);
-                    }
-                }
-                const float lh = en.x, lw = en.y;
-                const float hh = 1.f - lh, hw = 1.f - lw;
-                const float w1 = hh * hw * att, w2 = hh * lw * att, w3 = lh * hw * att, w4 = lh * lw * att;
-                const unsigned grow = G_s + (unsigned)q * (kD * 4);
-                const float4 g0 = lds4(grow + c0 * 16), g1 = lds4(grow + c1 * 16);
-#define MSDA_CH(G, K, F)                                              \
-    {                                                                 \
-        const float gc = G.F;                                         \
-        const float dh = fmaf(lw, dd[K].F, dH[K].F);                  \
-        const float tp = fmaf(lw, dW[K].F, v00[K].F);                 \
-        const float dw = fmaf(lh, dd[K].F, dW[K].F);                  \
-        s_a = fmaf(gc, fmaf(lh, dh, tp), s_a);                        \
-        s_h = fmaf(gc, dh, s_h);                                      \
-        s_w = fmaf(gc, dw, s_w);                                      \
-        a00[K].F = fmaf(w1, gc, a00[K].F);                            \
-        a01[K].F = fmaf(w2, gc, a01[K].F);                            \
-        a10[K].F = fmaf(w3, gc, a10[K].F);                            \
-        a11[K].F = fmaf(w4, gc, a11[K].F);                            \
+#define MSDA_FLUSH()                                                                                   \
+    {                                                                                                  \
+        if (inmask & 1) red_add_v4(gp, a00.lo.x, a00.lo.y, a00.hi.x, a00.hi.y);                        \
+        if (inmask & 2) red_add_v4(gp + o01, a01.lo.x, a01.lo.y, a01.hi.x, a01.hi.y);                  \
+        if (inmask & 4) red_add_v4(gp + o10, a10.lo.x, a10.lo.y, a10.hi.x, a10.hi.y);                  \
+        if (inmask & 8) red_add_v4(gp + o11, a11.lo.x, a11.lo.y, a11.hi.x, a11.hi.y);                  \
     }
-                MSDA_CH(g0, 0, x) MSDA_CH(g0, 0, y) MSDA_CH(g0, 0, z) MSDA_CH(g0, 0, w)
-                MSDA_CH(g1, 1, x) MSDA_CH(g1, 1, y) MSDA_CH(g1, 1, z) MSDA_CH(g1, 1, w)
-#undef MSDA_CH
+
+        // one sample: EN = its sorted entry, GR = its grad_out chunk (both already in registers)
+#define MSDA_SAMPLE(EN, GR, ACTIVE)                                                                                \
+    {                                                                                                              \
+        float s_a = 0.f, s_h = 0.f, s_w = 0.f, att_v = 0.f;                                                        \
+        int sidx = 0;                                                                                              \
+        if (ACTIVE) {                                                                                              \
+            const int packed = __float_as_int(EN.w);                                                               \
+            const int cell = packed >> 20;                                                                         \
+            sidx = (packed & 0xffff) * qstride + ((packed >> 16) & 0xf);                                           \
+            att_v = EN.z;                                                                                          \
+            if (cell != cur) {                                                                                     \
+                MSDA_FLUSH()                                                                                       \
+                a00 = a01 = a10 = a11 = {z2, z2};                                                                  \
+                cur = cell;                                                                                        \
+                const int cy = cell >> cs, cx = cell & ((1 << cs) - 1); /* padded coords of the top-left neighbour */ \
+                inmask = ((cy >= 1 && cx >= 1) ? 1 : 0) | ((cy >= 1 && cx <= W - 1) ? 2 : 0) |                     \
+                         ((cy <= H - 1 && cx >= 1) ? 4 : 0) | ((cy <= H - 1 && cx <= W - 1) ? 8 : 0);              \
+                gp = gbase + ((cy - 1) * W + cx - 1) * pix;                                                        \
+                const float4 *vr = Vj + (cy * Wp + cx) * 8;                                                        \
+                const f4p t00 = pk(vr[0]), t01 = pk(vr[8]), t10 = pk(vr[Wp * 8]), t11 = pk(vr[Wp * 8 + 8]);        \
+                v00 = t00;                                                                                         \
+                dW = psub(t01, t00);                                                                               \
+                dH = psub(t10, t00);                                                                               \
+                dd = psub(psub(t11, t10), dW);                                                                     \
+            }                                                                                                      \
+            const float lh = EN.x, lw = EN.y;                                                                      \
+            const float ah = (1.f - lh) * att_v, al = lh * att_v, hw = 1.f - lw;                                   \
+            const float2 lh2 = make_float2(lh, lh), lw2 = make_float2(lw, lw);                                     \
+            const float2 w1 = make_float2(ah * hw, ah * hw), w2 = make_float2(ah * lw, ah * lw);                   \
+            const float2 w3 = make_float2(al * hw, al * hw), w4 = make_float2(al * lw, al * lw);                   \
+            const f4p g = pk(GR);                                                                                  \
+            const float2 dh0 = __ffma2_rn(lw2, dd.lo, dH.lo), dh1 = __ffma2_rn(lw2, dd.hi, dH.hi);                 \
+            const float2 tp0 = __ffma2_rn(lw2, dW.lo, v00.lo), tp1 = __ffma2_rn(lw2, dW.hi, v00.hi);               \
+            const float2 dw0 = __ffma2_rn(lh2, dd.lo, dW.lo), dw1 = __ffma2_rn(lh2, dd.hi, dW.hi);                 \
+            const float2 pa = __ffma2_rn(g.hi, __ffma2_rn(lh2, dh1, tp1), __fmul2_rn(g.lo, __ffma2_rn(lh2, dh0, tp0))); \
+            const float2 ph = __ffma2_rn(g.hi, dh1, __fmul2_rn(g.lo, dh0));                                        \
+            const float2 pw = __ffma2_rn(g.hi, dw1, __fmul2_rn(g.lo, dw0));                                        \
+            a00.lo = __ffma2_rn(w1, g.lo, a00.lo); a00.hi = __ffma2_rn(w1, g.hi, a00.hi);                          \
+            a01.lo = __ffma2_rn(w2, g.lo, a01.lo); a01.hi = __ffma2_rn(w2, g.hi, a01.hi);                          \
+            a10.lo = __ffma2_rn(w3, g.lo, a10.lo); a10.hi = __ffma2_rn(w3, g.hi, a10.hi);                          \
+            a11.lo = __ffma2_rn(w4, g.lo, a11.lo); a11.hi = __ffma2_rn(w4, g.hi, a11.hi);                          \
+            s_a = pa.x + pa.y;                                                                                     \
+            s_h = ph.x + ph.y;                                                                                     \
+            s_w = pw.x + pw.y;                                                                                     \
+        }                                                                                                          \
+        /* 8-lane transposed reduction of (s_a, s_h, s_w): 4 shuffles; lane 0 ends with sum(a), lane 1 sum(h), lane 2 sum(w) */ \
+        float x = (j & 1) ? s_h : s_a;                                                                             \
+        x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1);                                                 \
+        s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);                                                               \
+        float keep = (j & 2) ? s_w : x;                                                                            \
+        keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2);                                                \
+        keep += __shfl_xor_sync(0xffffffffu, keep, 4);                                                             \
+        if ((ACTIVE) && j < 3) res_base[sidx * res_stride] = keep * res_scale * (j == 0 ? 1.f : att_v);            \
+    }
+
+        // software pipeline, unrolled by two so the prefetched registers ping-pong without moves
+        float4 enA = make_float4(0.f, 0.f, 0.f, 0.f), gA = enA, enB = enA, gB = enA;
+        if (e_lo < e_hi) {
+            enA = ent[e_lo];
+            gA = ldg4(gobase + (__float_as_int(enA.w) & 0xffff) * pix);
+        }
+        for (int it = 0; it < iters; it += 2) {
+            const int e = e_lo + it;
+            if (e + 1 < e_hi) {
+                enB = ent[e + 1];
+                gB = ldg4(gobase + (__float_as_int(enB.w) & 0xffff) * pix);
             }
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                s_a += __shfl_xor_sync(0xffffffffu, s_a, o);
-                s_h += __shfl_xor_sync(0xffffffffu, s_h, o);
-                s_w += __shfl_xor_sync(0xffffffffu, s_w, o);
-            }
-            if (active) {
-                const long long s = out0 + (long long)q * sp.M * LP + p;
-                if (sub == 0) *reinterpret_cast<float2 *>(grad_loc + 2 * s) = make_float2(Wf * att * s_w, Hf * att * s_h);
-                if (sub == 1) grad_attn[s] = s_a;
+            MSDA_SAMPLE(enA, gA, e < e_hi)
+            if (it + 1 < iters) {
+                if (e + 2 < e_hi) {
+                    enA = ent[e + 2];
+                    gA = ldg4(gobase + (__float_as_int(enA.w) & 0xffff) * pix);
+                }
+                MSDA_SAMPLE(enB, gB, e + 1 < e_hi)
             }
         }
-        flush();
+        if (cur >= 0) MSDA_FLUSH()
+#undef MSDA_SAMPLE
+#undef MSDA_FLUSH
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -267,10 +319,21 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem)
         sp.H[l] = p.table.H[l];
         sp.W[l] = p.table.W[l];
         sp.start[l] = p.table.start[l];
-        if ((long long)(sp.H[l] + 1) * (sp.W[l] + 1) > kMaxCells) return false;
+        int cs = 0;
+        while ((1 << cs) < sp.W[l] + 1) ++cs;
+        sp.cshift[l] = cs;
+        if (((long long)(sp.H[l] + 1) << cs) > kMaxCells) return false;
+        if ((long long)(sp.H[l] + 2) * (sp.W[l] + 2) * p.M * kD >= (1LL << 31)) return false;  // 32-bit row offsets
+    }
+    sp.vrows_max = 0;
+    for (int l = 0; l < p.L; ++l) {
+        const int rows = (sp.H[l] + 2) * (sp.W[l] + 2);
+        if (rows > sp.vrows_max) sp.vrows_max = rows;
+        if ((long long)sp.H[l] * sp.W[l] >= 65536) return false;
+        sp.wrecip[l] = (unsigned)((0x100000000ULL + sp.W[l] - 1) / sp.W[l]);
     }
     sp.units = (long long)p.N * p.M * p.L;
-    smem = (size_t)p.Lq * 8 * 16 + (size_t)p.Lq * p.P * 16 + (kMaxCells + 8 + 32) * sizeof(int);
+    smem = (size_t)sp.vrows_max * 8 * 16 + (size_t)p.Lq * p.P * 16 + (kMaxCells + 8 + 32) * sizeof(int);
     return smem <= (size_t)p.smem_optin;
 }
 
@@ -294,10 +357,11 @@ cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st
         if (e != cudaSuccess) return e;
     }
     if (sp.units == 0 || p.Lq == 0) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(bwd_sorted32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = p.P == 4 ? bwd_sorted32_kernel<4> : bwd_sorted32_kernel<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)(sp.units < p.sm_count ? sp.units : p.sm_count);
-    bwd_sorted32_kernel<<<grid, kThreads, smem, st>>>((const float *)p.value, (const float *)p.loc, (const float *)p.attn,
+    kern<<<grid, kThreads, smem, st>>>((const float *)p.value, (const float *)p.loc, (const float *)p.attn,
                                                       (const float *)io.grad_out, (float *)io.grad_value, (float *)io.grad_loc,
                                                       (float *)io.grad_attn, sp);
     count_launch();

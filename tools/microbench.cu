@@ -190,6 +190,23 @@ __global__ void __launch_bounds__(1024, 1) ffma_only(float *out, int iters, floa
     if (t == 1.2345f) out[0] = t;
 }
 
+// (h2) packed FFMA2 (fma.rn.f32x2) issue rate: 16 independent packed FMAs per iteration
+__global__ void __launch_bounds__(1024, 1) ffma2_only(float *out, int iters, float x)
+{
+    float2 a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = make_float2(threadIdx.x + k, threadIdx.x - k);
+    const float2 xx = make_float2(x, x);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = __ffma2_rn(a[k], xx, a[(k + 1) & 15]);
+    }
+    float t = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t += a[k].x + a[k].y;
+    if (t == 1.2345f) out[0] = t;
+}
+
 template <typename F> float time_ms(F launch, int reps = 5)
 {
     cudaEvent_t e0, e1;
@@ -266,5 +283,7 @@ int main()
     printf("%-44s %8.3f ms  %8.2f warp-SHFL/clk/SM\n", "g  SHFL.BFLY only", ms, (double)32 * ITERS * 4 / (ms * 1e-3) / (clk_khz * 1e3));
     ms = time_ms([&] { ffma_only<<<sms, 1024>>>(out, ITERS, 1.0001f); });
     printf("%-44s %8.3f ms  %8.2f warp-FFMA/clk/SM\n", "h  FFMA only", ms, (double)32 * ITERS * 16 / (ms * 1e-3) / (clk_khz * 1e3));
+    ms = time_ms([&] { ffma2_only<<<sms, 1024>>>(out, ITERS, 1.0001f); });
+    printf("%-44s %8.3f ms  %8.2f warp-FFMA2/clk/SM (x2 FMAs each)\n", "h2 FFMA2 only", ms, (double)32 * ITERS * 16 / (ms * 1e-3) / (clk_khz * 1e3));
     return 0;
 }
