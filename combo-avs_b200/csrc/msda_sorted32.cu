@@ -16,6 +16,7 @@
 // A lane group is 8 lanes x 4 channels (one 128-byte row per LDS.128 phase: conflict-free); the three per-sample sums
 // are reduced over the 8 lanes with a transposed butterfly (4 shuffles instead of 9).
 #include <cmath>
+#include <cstdlib>
 
 #include "msda_kernels.h"
 
@@ -23,9 +24,8 @@ namespace msda {
 namespace {
 
 constexpr int kD = 32;
-constexpr int kThreads = 768;
-constexpr int kGroups = kThreads / 8;
-constexpr int kRounds = 6;          // samples per thread held in registers between the count and the fill pass
+constexpr int kMaxSamples = 4608;    // Lq*P per level that the register-resident count/fill passes can hold
+//         // samples per thread held in registers between the count and the fill pass
 constexpr int kMaxCells = 1024;     // cell-grid size per level, scanned two per thread
 
 struct SortParams {
@@ -61,12 +61,27 @@ __device__ __forceinline__ float floor_magic(float x, int &i)
     return t - 12582912.f;
 }
 
-template <int P_T>
+// Pin a value in a register: ptxas otherwise re-derives "cheap" values (special registers, parameter loads, the
+// shared-window base) inside the hot loop, paying an issue slot each time.
+__device__ __forceinline__ void pin(int &x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void pin(float &x) { asm volatile("" : "+f"(x)); }
+template <typename T> __device__ __forceinline__ void pin(T *&x) { asm volatile("" : "+l"(x)); }
+__device__ __forceinline__ float4 lds4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int P_T, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1)
 bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ loc, const float *__restrict__ attn,
                     const float *__restrict__ grad_out, float *__restrict__ grad_value, float *__restrict__ grad_loc,
                     float *__restrict__ grad_attn, const __grid_constant__ SortParams sp)
 {
+    constexpr int kGroups = kThreads / 8, kRounds = (kMaxSamples + kThreads - 1) / kThreads;
+    static_assert(2 * kThreads >= kMaxCells, "scan covers two cells per thread");
     extern __shared__ float4 smem4[];
     const int Lq = sp.Lq, P = P_T > 0 ? P_T : sp.P, EP = Lq * P, LP = sp.L * P;
     float4 *V4 = smem4;                                   // zero-padded value slab of the current level: (H+2) x (W+2) rows
@@ -74,7 +89,11 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
     int *cell_off = reinterpret_cast<int *>(ent + EP);    // kMaxCells + 1 counters -> exclusive offsets
     int *warp_tot = cell_off + kMaxCells + 8;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int grp = tid >> 3, j = tid & 7;                // 8 lanes per sample, lane j owns channels [4j, 4j+4)
+    const int grp = tid >> 3;
+    int j = tid & 7;                                      // 8 lanes per sample, lane j owns channels [4j, 4j+4)
+    pin(j);
+    unsigned ent_s = (unsigned)__cvta_generic_to_shared(ent);
+    pin(ent_s);
     const int pix = sp.M * kD;
     const int qstride = sp.M * LP;  // samples between consecutive queries of one head
 
@@ -207,11 +226,15 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         const float *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD + j * 4;
         float *gbase = grad_value + lvl_row + j * 4;
         const int o01 = pix, o10 = W * pix, o11 = (W + 1) * pix;
-        const float4 *Vj = V4 + j;            // this lane's 16-byte chunk of padded row r is Vj[r*8]
+        unsigned Vj_s = (unsigned)__cvta_generic_to_shared(V4 + j);  // this lane's 16-byte chunk of padded row r: Vj_s + r*128
+        pin(Vj_s);
+        int qs = qstride, pixv = pix, Wv = W, Wpb = Wp * (kD * 4);
+        pin(qs); pin(pixv); pin(Wv); pin(Wpb);
         // lanes 0..2 of a group store the three per-sample results: lane 0 grad_attn, lane 1 grad_loc.y, lane 2 grad_loc.x
         float *res_base = j == 0 ? gatt : gloc + (j == 1 ? 1 : 0);
-        const int res_stride = j == 0 ? 1 : 2;
-        const float res_scale = j == 0 ? 1.f : (j == 1 ? Hf : Wf);
+        int res_stride = j == 0 ? 1 : 2;
+        float res_scale = j == 0 ? 1.f : (j == 1 ? Hf : Wf);
+        pin(res_base); pin(res_stride); pin(res_scale); pin(gobase); pin(gbase);
         int cur = -1, inmask = 0;
         float *gp = gbase;         // grad_value row of the current cell's top-left neighbour (this lane's chunk)
         f4p v00, dW, dH, dd;       // V00, V01-V00, V10-V00, V11-V10-V01+V00 (this lane's 4 channels)
@@ -235,18 +258,18 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         if (ACTIVE) {                                                                                              \
             const int packed = __float_as_int(EN.w);                                                               \
             const int cell = packed >> 20;                                                                         \
-            sidx = (packed & 0xffff) * qstride + ((packed >> 16) & 0xf);                                           \
+            sidx = (packed & 0xffff) * qs + ((packed >> 16) & 0xf);                                                \
             att_v = EN.z;                                                                                          \
             if (cell != cur) {                                                                                     \
                 MSDA_FLUSH()                                                                                       \
                 a00 = a01 = a10 = a11 = {z2, z2};                                                                  \
                 cur = cell;                                                                                        \
                 const int cy = cell >> cs, cx = cell & ((1 << cs) - 1); /* padded coords of the top-left neighbour */ \
-                inmask = ((cy >= 1 && cx >= 1) ? 1 : 0) | ((cy >= 1 && cx <= W - 1) ? 2 : 0) |                     \
-                         ((cy <= H - 1 && cx >= 1) ? 4 : 0) | ((cy <= H - 1 && cx <= W - 1) ? 8 : 0);              \
-                gp = gbase + ((cy - 1) * W + cx - 1) * pix;                                                        \
-                const float4 *vr = Vj + (cy * Wp + cx) * 8;                                                        \
-                const f4p t00 = pk(vr[0]), t01 = pk(vr[8]), t10 = pk(vr[Wp * 8]), t11 = pk(vr[Wp * 8 + 8]);        \
+                inmask = ((cy >= 1 && cx >= 1) ? 1 : 0) | ((cy >= 1 && cx <= Wv - 1) ? 2 : 0) |                     \
+                         ((cy <= H - 1 && cx >= 1) ? 4 : 0) | ((cy <= H - 1 && cx <= Wv - 1) ? 8 : 0);              \
+                gp = gbase + ((cy - 1) * Wv + cx - 1) * pixv;                                                      \
+                const unsigned vr = Vj_s + (unsigned)(cy * Wpb + cx * (kD * 4));                                   \
+                const f4p t00 = pk(lds4(vr)), t01 = pk(lds4(vr + kD * 4)), t10 = pk(lds4(vr + Wpb)), t11 = pk(lds4(vr + Wpb + kD * 4)); \
                 v00 = t00;                                                                                         \
                 dW = psub(t01, t00);                                                                               \
                 dH = psub(t10, t00);                                                                               \
@@ -285,20 +308,20 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         // software pipeline, unrolled by two so the prefetched registers ping-pong without moves
         float4 enA = make_float4(0.f, 0.f, 0.f, 0.f), gA = enA, enB = enA, gB = enA;
         if (e_lo < e_hi) {
-            enA = ent[e_lo];
-            gA = ldg4(gobase + (__float_as_int(enA.w) & 0xffff) * pix);
+            enA = lds4(ent_s + e_lo * 16);
+            gA = ldg4(gobase + (__float_as_int(enA.w) & 0xffff) * pixv);
         }
         for (int it = 0; it < iters; it += 2) {
             const int e = e_lo + it;
             if (e + 1 < e_hi) {
-                enB = ent[e + 1];
-                gB = ldg4(gobase + (__float_as_int(enB.w) & 0xffff) * pix);
+                enB = lds4(ent_s + (e + 1) * 16);
+                gB = ldg4(gobase + (__float_as_int(enB.w) & 0xffff) * pixv);
             }
             MSDA_SAMPLE(enA, gA, e < e_hi)
             if (it + 1 < iters) {
                 if (e + 2 < e_hi) {
-                    enA = ent[e + 2];
-                    gA = ldg4(gobase + (__float_as_int(enA.w) & 0xffff) * pix);
+                    enA = lds4(ent_s + (e + 2) * 16);
+                    gA = ldg4(gobase + (__float_as_int(enA.w) & 0xffff) * pixv);
                 }
                 MSDA_SAMPLE(enB, gB, e + 1 < e_hi)
             }
@@ -313,7 +336,7 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
 bool make_params(const Problem &p, SortParams &sp, size_t &smem)
 {
     if (!(p.dtype == 0 && p.loc_dtype == 0 && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
-    if (p.Lq < 1 || p.Lq > 65535 || p.P > 16 || (long long)p.Lq * p.P > (long long)kRounds * kThreads) return false;
+    if (p.Lq < 1 || p.Lq > 65535 || p.P > 16 || (long long)p.Lq * p.P > kMaxSamples) return false;
     sp.L = p.L; sp.P = p.P; sp.S = p.S; sp.M = p.M; sp.Lq = p.Lq;
     for (int l = 0; l < p.L; ++l) {
         sp.H[l] = p.table.H[l];
@@ -357,7 +380,11 @@ cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st
         if (e != cudaSuccess) return e;
     }
     if (sp.units == 0 || p.Lq == 0) return cudaSuccess;
-    auto kern = p.P == 4 ? bwd_sorted32_kernel<4> : bwd_sorted32_kernel<0>;
+    static const int threads_env = [] { const char *v = getenv("MSDA_SORTED_THREADS"); return v ? atoi(v) : 0; }();
+    const int threads = threads_env == 640 ? 640 : threads_env == 896 ? 896 : threads_env == 1024 ? 1024 : 768;
+    auto kern = p.P == 4 ? (threads == 640 ? bwd_sorted32_kernel<4, 640> : threads == 896 ? bwd_sorted32_kernel<4, 896> : threads == 1024 ? bwd_sorted32_kernel<4, 1024> : bwd_sorted32_kernel<4, 768>)
+                         : bwd_sorted32_kernel<0, 768>;
+    const int kThreads = p.P == 4 ? threads : 768;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)(sp.units < p.sm_count ? sp.units : p.sm_count);
