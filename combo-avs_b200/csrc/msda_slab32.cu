@@ -15,6 +15,7 @@
 // number of passes per slab that balances N*M*passes units over the SMs; each persistent CTA (one per SM) owns a
 // contiguous unit range, so consecutive units reuse the resident slab.
 #include <cmath>
+#include <cstdlib>
 
 #include "msda_kernels.h"
 
@@ -30,6 +31,8 @@ struct SlabParams {
     int prow0[kMaxLevels];    // first padded row of the level inside the slab; padded pitch is W+2
     float hmax[kMaxLevels];   // largest float below H (clamp bound that leaves in-range samples untouched)
     float wmax[kMaxLevels];
+    unsigned wrecip[kMaxLevels];  // ceil(2^32 / W): pixel / W == umulhi(pixel, wrecip) for pixel < 2^16
+    unsigned precip;          // ceil(2^32 / (3*L*P/4)) for the metadata staging index split
     int padded_rows;          // total rows of the padded slab
     int qpp;                  // queries per pass
     int pps;                  // passes per slab
@@ -59,7 +62,7 @@ __device__ __forceinline__ void load_slab(float4 *slab, const float *__restrict_
         float4 *ldst = slab + (size_t)(sp.prow0[l] + (W + 2) + 1) * 8;
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
             const int pix = i >> 3, c = i & 7;
-            const int y = pix / W, x = pix - y * W;
+            const int y = (int)__umulhi((unsigned)pix, sp.wrecip[l]), x = pix - y * W;
             cp_async16(ldst + (size_t)(y * (W + 2) + x) * 8 + c, lsrc + (long long)pix * pixf + c * 4);
         }
     }
@@ -85,20 +88,36 @@ __device__ __forceinline__ void stage_meta(float *meta, const float *__restrict_
     const int m = (int)(nm - n * sp.M);
     const int pieces = (3 * LP) >> 2, loc_pieces = LP >> 1;
     const int total = cnt * pieces;
+    const long long qm0 = (n * sp.Lq + q0) * sp.M + m;
+    const float *lbase = loc + qm0 * (2 * LP), *abase = attn + qm0 * LP;
+    const int lstride = sp.M * 2 * LP, astride = sp.M * LP;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int ql = i / pieces, pc = i - ql * pieces;
-        const long long qm = (n * sp.Lq + q0 + ql) * sp.M + m;
-        const float *src = pc < loc_pieces ? loc + qm * (2 * LP) + pc * 4 : attn + qm * LP + (pc - loc_pieces) * 4;
+        const int ql = (int)__umulhi((unsigned)i, sp.precip), pc = i - ql * pieces;
+        const float *src = pc < loc_pieces ? lbase + ql * lstride + pc * 4 : abase + ql * astride + (pc - loc_pieces) * 4;
         cp_async16(meta + ql * (3 * LP) + pc * 4, src);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-template <int P_T, bool STAGE>
-__global__ void __launch_bounds__(512, 1)
+// packed fp32x2 (FFMA2 on sm_100a): halves the issue slots of the interpolation math
+struct f4p {
+    float2 lo, hi;
+};
+__device__ __forceinline__ float4 lds4(unsigned addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void pin(int &x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
+
+template <int P_T, bool STAGE, int SPLIT>
+__global__ void __launch_bounds__(SPLIT == 4 ? 768 : 512, 1)
 fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc, const float *__restrict__ attn,
                   float *__restrict__ out, const __grid_constant__ SlabParams sp)
 {
+    constexpr int CH = 8 / SPLIT;  // 16-byte chunks (4 channels) per lane
     extern __shared__ float4 slab[];
     const int P = P_T > 0 ? P_T : sp.P;
     const int LP = sp.L * P;
@@ -106,11 +125,19 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
     const int meta_stride = sp.qpp * 3 * LP;
     for (int i = threadIdx.x; i < sp.padded_rows * 8; i += blockDim.x) slab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long u_lo = sp.units * blockIdx.x / gridDim.x, u_hi = sp.units * (blockIdx.x + 1) / gridDim.x;
-    const int pair = threadIdx.x >> 1, half = threadIdx.x & 1;
-    unsigned off[4];  // byte offset of this lane's k-th chunk inside a row
+    int ql = threadIdx.x / SPLIT;
+    const int part = threadIdx.x % SPLIT;
+    pin(ql);
+    // lane (ql, part) owns chunks [part*CH, part*CH+CH); its k-th load reads chunk part*CH + ((k + ql) % CH), so the 8 lanes of
+    // every LDS.128 phase touch 8 different chunks = all 32 banks, whatever rows they gather: conflict-free
+    unsigned off[CH];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) off[k] = (half * 4 + ((k + pair) & 3)) * 16;
-    const unsigned slab_s = (unsigned)__cvta_generic_to_shared(slab);
+    for (int k = 0; k < CH; ++k) {
+        off[k] = (part * CH + ((k + ql) % CH)) * 16;
+        pin(off[k]);
+    }
+    unsigned slab_s = (unsigned)__cvta_generic_to_shared(slab);
+    pin(slab_s);
     long long resident = -1;
     auto pass_range = [&](long long u, long long &nm, int &q0, int &cnt) {
         nm = u / sp.pps;
@@ -139,16 +166,16 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
             pass_range(u + 1, nm2, q02, cnt2);
             stage_meta(meta0 + ((u + 1 - u_lo) & 1) * meta_stride, loc, attn, sp, LP, nm2, q02, cnt2);
         }
-        if (pair >= cnt) continue;
-        const int q = q0 + pair;
+        if (ql >= cnt) continue;
+        const int q = q0 + ql;
         const long long n = nm / sp.M;
         const int m = (int)(nm - n * sp.M);
         const long long qm = (n * sp.Lq + q) * sp.M + m;
-        const float2 *loc2 = STAGE ? reinterpret_cast<const float2 *>(meta + pair * 3 * LP) : reinterpret_cast<const float2 *>(loc) + qm * LP;
-        const float *att = STAGE ? meta + pair * 3 * LP + 2 * LP : attn + qm * LP;
-        float4 acc[4];
+        const float2 *loc2 = STAGE ? reinterpret_cast<const float2 *>(meta + ql * 3 * LP) : reinterpret_cast<const float2 *>(loc) + qm * LP;
+        const float *att = STAGE ? meta + ql * 3 * LP + 2 * LP : attn + qm * LP;
+        f4p acc[CH];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < CH; ++k) acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
         for (int l = 0; l < sp.L; ++l) {
             const float Hf = (float)sp.H[l], Wf = (float)sp.W[l];
             const float hmax = sp.hmax[l], wmax = sp.wmax[l];
@@ -171,27 +198,26 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
                     floor_split(wc, fw, x0);
                     const float lh = hc - fh, lw = wc - fw;
                     const float ahh = a * (1.f - lh), alh = a * lh, hw = 1.f - lw;
-                    const float w1 = ahh * hw, w2 = ahh * lw, w3 = alh * hw, w4 = alh * lw;
+                    const float w1s = ahh * hw, w2s = ahh * lw, w3s = alh * hw, w4s = alh * lw;
+                    const float2 w1 = make_float2(w1s, w1s), w2 = make_float2(w2s, w2s), w3 = make_float2(w3s, w3s), w4 = make_float2(w4s, w4s);
                     const unsigned r00 = lvl_s + (unsigned)(y0 * pitch + x0) * kRowBytes;
                     const unsigned r10 = r00 + pitch_b;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float4 v1, v2, v3, v4;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v1.x), "=f"(v1.y), "=f"(v1.z), "=f"(v1.w) : "r"(r00 + off[k]));
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+128];" : "=f"(v2.x), "=f"(v2.y), "=f"(v2.z), "=f"(v2.w) : "r"(r00 + off[k]));
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v3.x), "=f"(v3.y), "=f"(v3.z), "=f"(v3.w) : "r"(r10 + off[k]));
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+128];" : "=f"(v4.x), "=f"(v4.y), "=f"(v4.z), "=f"(v4.w) : "r"(r10 + off[k]));
-                        acc[k].x = fmaf(w1, v1.x, fmaf(w2, v2.x, fmaf(w3, v3.x, fmaf(w4, v4.x, acc[k].x))));
-                        acc[k].y = fmaf(w1, v1.y, fmaf(w2, v2.y, fmaf(w3, v3.y, fmaf(w4, v4.y, acc[k].y))));
-                        acc[k].z = fmaf(w1, v1.z, fmaf(w2, v2.z, fmaf(w3, v3.z, fmaf(w4, v4.z, acc[k].z))));
-                        acc[k].w = fmaf(w1, v1.w, fmaf(w2, v2.w, fmaf(w3, v3.w, fmaf(w4, v4.w, acc[k].w))));
+                    for (int k = 0; k < CH; ++k) {
+                        const float4 v1 = lds4(r00 + off[k]), v2 = lds4(r00 + off[k] + kRowBytes);
+                        const float4 v3 = lds4(r10 + off[k]), v4 = lds4(r10 + off[k] + kRowBytes);
+                        acc[k].lo = __ffma2_rn(w1, make_float2(v1.x, v1.y), __ffma2_rn(w2, make_float2(v2.x, v2.y),
+                                    __ffma2_rn(w3, make_float2(v3.x, v3.y), __ffma2_rn(w4, make_float2(v4.x, v4.y), acc[k].lo))));
+                        acc[k].hi = __ffma2_rn(w1, make_float2(v1.z, v1.w), __ffma2_rn(w2, make_float2(v2.z, v2.w),
+                                    __ffma2_rn(w3, make_float2(v3.z, v3.w), __ffma2_rn(w4, make_float2(v4.z, v4.w), acc[k].hi))));
                     }
                 }
             }
         }
         float *o = out + qm * kD;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) *reinterpret_cast<float4 *>(o + (off[k] >> 2)) = acc[k];
+        for (int k = 0; k < CH; ++k)
+            *reinterpret_cast<float4 *>(o + (off[k] >> 2)) = make_float4(acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -216,8 +242,15 @@ void plan_passes(int Lq, long long slabs, int ctas, int max_pairs, int &qpp, int
     }
 }
 
+int slab_split()
+{
+    static const int v = [] { const char *e = getenv("MSDA_SLAB_SPLIT"); return e && atoi(e) == 4 ? 4 : 2; }();
+    return v;
+}
+
 bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &threads, int &grid, bool &stage)
 {
+    const int split = slab_split();
     if (!(p.dtype == 0 && p.loc_dtype == 0 && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
     sp.L = p.L; sp.P = p.P; sp.S = p.S; sp.M = p.M; sp.Lq = p.Lq;
     int rows = 0;
@@ -228,6 +261,8 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
         sp.prow0[l] = rows;
         sp.hmax[l] = nextafterf((float)sp.H[l], 0.f);
         sp.wmax[l] = nextafterf((float)sp.W[l], 0.f);
+        sp.wrecip[l] = (unsigned)((0x100000000ULL + sp.W[l] - 1) / sp.W[l]);
+        if ((long long)sp.H[l] * sp.W[l] >= 65536) return false;
         rows += (sp.H[l] + 2) * (sp.W[l] + 2);
         if (rows > (1 << 20)) return false;
     }
@@ -237,12 +272,14 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
     const long long slabs = (long long)p.N * p.M;
     grid = (int)(slabs * 16 < p.sm_count ? slabs * 16 : p.sm_count);
     if (grid < 1) grid = 1;
-    plan_passes(p.Lq, slabs, grid, 256, sp.qpp, sp.pps);
+    const int max_threads = split == 4 ? 768 : 512;
+    plan_passes(p.Lq, slabs, grid, max_threads / split, sp.qpp, sp.pps);
     sp.units = slabs * sp.pps;
-    threads = ((sp.qpp * 2 + 31) / 32) * 32;
-    if (threads > 512) threads = 512;
+    threads = ((sp.qpp * split + 31) / 32) * 32;
+    if (threads > max_threads) threads = max_threads;
     // metadata staging (two buffers of qpp rows of 3*L*P floats) when 16-byte pieces line up and it fits
     const int LP = p.L * p.P;
+    sp.precip = LP >= 4 ? (unsigned)((0x100000000ULL + (3 * LP / 4) - 1) / (3 * LP / 4)) : 0;
     const size_t meta_bytes = 2 * (size_t)sp.qpp * 3 * LP * sizeof(float);
     stage = (LP % 4 == 0) && smem_bytes + meta_bytes <= (size_t)p.smem_optin;
     if (stage) smem_bytes += meta_bytes;
@@ -268,8 +305,11 @@ cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st)
     bool stage;
     if (!make_params(p, sp, smem, threads, grid, stage)) return cudaErrorInvalidValue;
     if ((long long)p.N * p.M * p.Lq == 0) return cudaSuccess;
-    auto kern = p.P == 4 ? (stage ? fwd_slab32_kernel<4, true> : fwd_slab32_kernel<4, false>)
-                         : (stage ? fwd_slab32_kernel<0, true> : fwd_slab32_kernel<0, false>);
+    const bool s4 = slab_split() == 4;
+    auto kern = p.P == 4 ? (stage ? (s4 ? fwd_slab32_kernel<4, true, 4> : fwd_slab32_kernel<4, true, 2>)
+                                  : (s4 ? fwd_slab32_kernel<4, false, 4> : fwd_slab32_kernel<4, false, 2>))
+                         : (stage ? (s4 ? fwd_slab32_kernel<0, true, 4> : fwd_slab32_kernel<0, true, 2>)
+                                  : (s4 ? fwd_slab32_kernel<0, false, 4> : fwd_slab32_kernel<0, false, 2>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, threads, smem, st>>>((const float *)p.value, (const float *)p.loc, (const float *)p.attn, (float *)out, sp);

@@ -74,14 +74,18 @@ __device__ __forceinline__ float4 lds4(unsigned addr)
     return v;
 }
 
-template <int P_T, int kThreads>
-__global__ void __launch_bounds__(kThreads, 1)
+__host__ __device__ constexpr int threads_for_split(int split) { return split == 8 ? 768 : split == 4 ? 512 : 384; }
+
+// SPLIT lanes share one sample; each lane owns CH = 8/SPLIT chunks of 4 channels.
+template <int P_T, int SPLIT>
+__global__ void __launch_bounds__(threads_for_split(SPLIT), 1)
 bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ loc, const float *__restrict__ attn,
                     const float *__restrict__ grad_out, float *__restrict__ grad_value, float *__restrict__ grad_loc,
                     float *__restrict__ grad_attn, const __grid_constant__ SortParams sp)
 {
-    constexpr int kGroups = kThreads / 8, kRounds = (kMaxSamples + kThreads - 1) / kThreads;
-    static_assert(2 * kThreads >= kMaxCells, "scan covers two cells per thread");
+    constexpr int kThreads = threads_for_split(SPLIT), CH = 8 / SPLIT;
+    constexpr int kGroups = kThreads / SPLIT, kRounds = (kMaxSamples + kThreads - 1) / kThreads;
+    constexpr int kCPT = (kMaxCells + kThreads - 1) / kThreads;  // cells scanned per thread
     extern __shared__ float4 smem4[];
     const int Lq = sp.Lq, P = P_T > 0 ? P_T : sp.P, EP = Lq * P, LP = sp.L * P;
     float4 *V4 = smem4;                                   // zero-padded value slab of the current level: (H+2) x (W+2) rows
@@ -89,9 +93,16 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
     int *cell_off = reinterpret_cast<int *>(ent + EP);    // kMaxCells + 1 counters -> exclusive offsets
     int *warp_tot = cell_off + kMaxCells + 8;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int grp = tid >> 3;
-    int j = tid & 7;                                      // 8 lanes per sample, lane j owns channels [4j, 4j+4)
+    const int grp = tid / SPLIT;
+    int j = tid % SPLIT;                                  // lane j of its sample group
     pin(j);
+    // slot k of this lane is chunk j*CH + ((k + grp) % CH): the 8 lanes of an LDS.128 phase then cover all 32 banks
+    int chf[CH];                                          // float offset of slot k inside a 32-channel row
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        chf[k] = (j * CH + ((k + grp) % CH)) * 4;
+        pin(chf[k]);
+    }
     unsigned ent_s = (unsigned)__cvta_generic_to_shared(ent);
     pin(ent_s);
     const int pix = sp.M * kD;
@@ -173,11 +184,16 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         }
         __syncthreads();
 
-        // ---- exclusive scan of the cell counters (<= 1024 cells, two per thread) -----------------------------------------
+        // ---- exclusive scan of the cell counters (<= kMaxCells cells, kCPT consecutive cells per thread) -------------------
         {
-            const int i0 = 2 * tid, i1 = 2 * tid + 1;
-            const int v0 = i0 < cells ? cell_off[i0] : 0, v1 = i1 < cells ? cell_off[i1] : 0;
-            int incl = v0 + v1;
+            int v[kCPT], sum = 0;
+#pragma unroll
+            for (int k = 0; k < kCPT; ++k) {
+                const int i = kCPT * tid + k;
+                v[k] = i < cells ? cell_off[i] : 0;
+                sum += v[k];
+            }
+            int incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -195,9 +211,13 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
                 if (lane < kThreads / 32) warp_tot[lane] = t;  // inclusive totals of warps
             }
             __syncthreads();
-            const int base = (wid > 0 ? warp_tot[wid - 1] : 0) + incl - (v0 + v1);
-            if (i0 < cells) cell_off[i0] = base;
-            if (i1 < cells) cell_off[i1] = base + v0;
+            int base = (wid > 0 ? warp_tot[wid - 1] : 0) + incl - sum;
+#pragma unroll
+            for (int k = 0; k < kCPT; ++k) {
+                const int i = kCPT * tid + k;
+                if (i < cells) cell_off[i] = base;
+                base += v[k];
+            }
             if (tid == kThreads - 1) cell_off[kMaxCells] = warp_tot[kThreads / 32 - 1];  // number of in-range samples
         }
         __syncthreads();
@@ -218,119 +238,150 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();  // sorted list complete, value slab landed
 
-        // ---- walk the sorted list: every 8-lane group owns a contiguous range of entries -----------------------------------
+        // ---- walk the sorted list: every SPLIT-lane group owns a contiguous range of entries -------------------------------
         const int E = cell_off[kMaxCells];
         const int e_lo = (int)((long long)E * grp / kGroups), e_hi = (int)((long long)E * (grp + 1) / kGroups);
         const int iters = (E + kGroups - 1) / kGroups;
-        // grad_out row of query q, this lane's chunk: gobase + q*pix; streamed from L2, prefetched one entry ahead
-        const float *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD + j * 4;
-        float *gbase = grad_value + lvl_row + j * 4;
+        // grad_out row of query q: gobase + q*pix (+ chf[k]); streamed from L2, prefetched one entry ahead
+        const float *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD;
+        float *gbase = grad_value + lvl_row;
         const int o01 = pix, o10 = W * pix, o11 = (W + 1) * pix;
-        unsigned Vj_s = (unsigned)__cvta_generic_to_shared(V4 + j);  // this lane's 16-byte chunk of padded row r: Vj_s + r*128
-        pin(Vj_s);
+        unsigned V_s = (unsigned)__cvta_generic_to_shared(V4);
+        pin(V_s);
         int qs = qstride, pixv = pix, Wv = W, Wpb = Wp * (kD * 4);
         pin(qs); pin(pixv); pin(Wv); pin(Wpb);
-        // lanes 0..2 of a group store the three per-sample results: lane 0 grad_attn, lane 1 grad_loc.y, lane 2 grad_loc.x
-        float *res_base = j == 0 ? gatt : gloc + (j == 1 ? 1 : 0);
-        int res_stride = j == 0 ? 1 : 2;
+        // result stores: SPLIT >= 4: lane 0 grad_attn, lane 1 grad_loc.y, lane 2 grad_loc.x; SPLIT == 2: lane 0 grad_loc (float2), lane 1 grad_attn
+        float *res_base = SPLIT >= 4 ? (j == 0 ? gatt : gloc + (j == 1 ? 1 : 0)) : (j == 0 ? gloc : gatt);
+        int res_stride = SPLIT >= 4 ? (j == 0 ? 1 : 2) : (j == 0 ? 2 : 1);
         float res_scale = j == 0 ? 1.f : (j == 1 ? Hf : Wf);
         pin(res_base); pin(res_stride); pin(res_scale); pin(gobase); pin(gbase);
         int cur = -1, inmask = 0;
-        float *gp = gbase;         // grad_value row of the current cell's top-left neighbour (this lane's chunk)
-        f4p v00, dW, dH, dd;       // V00, V01-V00, V10-V00, V11-V10-V01+V00 (this lane's 4 channels)
-        f4p a00, a01, a10, a11;    // grad_value accumulators of the four neighbour rows
+        float *gp = gbase;             // grad_value row of the current cell's top-left neighbour
+        f4p v00[CH], dW[CH], dH[CH], dd[CH];       // V00, V01-V00, V10-V00, V11-V10-V01+V00 per owned chunk
+        f4p a00[CH], a01[CH], a10[CH], a11[CH];    // grad_value accumulators of the four neighbour rows
         const float2 z2 = make_float2(0.f, 0.f);
-        a00 = a01 = a10 = a11 = {z2, z2};
+#pragma unroll
+        for (int k = 0; k < CH; ++k) a00[k] = a01[k] = a10[k] = a11[k] = {z2, z2};
 
-#define MSDA_FLUSH()                                                                                   \
-    {                                                                                                  \
-        if (inmask & 1) red_add_v4(gp, a00.lo.x, a00.lo.y, a00.hi.x, a00.hi.y);                        \
-        if (inmask & 2) red_add_v4(gp + o01, a01.lo.x, a01.lo.y, a01.hi.x, a01.hi.y);                  \
-        if (inmask & 4) red_add_v4(gp + o10, a10.lo.x, a10.lo.y, a10.hi.x, a10.hi.y);                  \
-        if (inmask & 8) red_add_v4(gp + o11, a11.lo.x, a11.lo.y, a11.hi.x, a11.hi.y);                  \
-    }
-
-        // one sample: EN = its sorted entry, GR = its grad_out chunk (both already in registers)
-#define MSDA_SAMPLE(EN, GR, ACTIVE)                                                                                \
-    {                                                                                                              \
-        float s_a = 0.f, s_h = 0.f, s_w = 0.f, att_v = 0.f;                                                        \
-        int sidx = 0;                                                                                              \
-        if (ACTIVE) {                                                                                              \
-            const int packed = __float_as_int(EN.w);                                                               \
-            const int cell = packed >> 20;                                                                         \
-            sidx = (packed & 0xffff) * qs + ((packed >> 16) & 0xf);                                                \
-            att_v = EN.z;                                                                                          \
-            if (cell != cur) {                                                                                     \
-                MSDA_FLUSH()                                                                                       \
-                a00 = a01 = a10 = a11 = {z2, z2};                                                                  \
-                cur = cell;                                                                                        \
-                const int cy = cell >> cs, cx = cell & ((1 << cs) - 1); /* padded coords of the top-left neighbour */ \
-                inmask = ((cy >= 1 && cx >= 1) ? 1 : 0) | ((cy >= 1 && cx <= Wv - 1) ? 2 : 0) |                     \
-                         ((cy <= H - 1 && cx >= 1) ? 4 : 0) | ((cy <= H - 1 && cx <= Wv - 1) ? 8 : 0);              \
-                gp = gbase + ((cy - 1) * Wv + cx - 1) * pixv;                                                      \
-                const unsigned vr = Vj_s + (unsigned)(cy * Wpb + cx * (kD * 4));                                   \
-                const f4p t00 = pk(lds4(vr)), t01 = pk(lds4(vr + kD * 4)), t10 = pk(lds4(vr + Wpb)), t11 = pk(lds4(vr + Wpb + kD * 4)); \
-                v00 = t00;                                                                                         \
-                dW = psub(t01, t00);                                                                               \
-                dH = psub(t10, t00);                                                                               \
-                dd = psub(psub(t11, t10), dW);                                                                     \
-            }                                                                                                      \
-            const float lh = EN.x, lw = EN.y;                                                                      \
-            const float ah = (1.f - lh) * att_v, al = lh * att_v, hw = 1.f - lw;                                   \
-            const float2 lh2 = make_float2(lh, lh), lw2 = make_float2(lw, lw);                                     \
-            const float2 w1 = make_float2(ah * hw, ah * hw), w2 = make_float2(ah * lw, ah * lw);                   \
-            const float2 w3 = make_float2(al * hw, al * hw), w4 = make_float2(al * lw, al * lw);                   \
-            const f4p g = pk(GR);                                                                                  \
-            const float2 dh0 = __ffma2_rn(lw2, dd.lo, dH.lo), dh1 = __ffma2_rn(lw2, dd.hi, dH.hi);                 \
-            const float2 tp0 = __ffma2_rn(lw2, dW.lo, v00.lo), tp1 = __ffma2_rn(lw2, dW.hi, v00.hi);               \
-            const float2 dw0 = __ffma2_rn(lh2, dd.lo, dW.lo), dw1 = __ffma2_rn(lh2, dd.hi, dW.hi);                 \
-            const float2 pa = __ffma2_rn(g.hi, __ffma2_rn(lh2, dh1, tp1), __fmul2_rn(g.lo, __ffma2_rn(lh2, dh0, tp0))); \
-            const float2 ph = __ffma2_rn(g.hi, dh1, __fmul2_rn(g.lo, dh0));                                        \
-            const float2 pw = __ffma2_rn(g.hi, dw1, __fmul2_rn(g.lo, dw0));                                        \
-            a00.lo = __ffma2_rn(w1, g.lo, a00.lo); a00.hi = __ffma2_rn(w1, g.hi, a00.hi);                          \
-            a01.lo = __ffma2_rn(w2, g.lo, a01.lo); a01.hi = __ffma2_rn(w2, g.hi, a01.hi);                          \
-            a10.lo = __ffma2_rn(w3, g.lo, a10.lo); a10.hi = __ffma2_rn(w3, g.hi, a10.hi);                          \
-            a11.lo = __ffma2_rn(w4, g.lo, a11.lo); a11.hi = __ffma2_rn(w4, g.hi, a11.hi);                          \
-            s_a = pa.x + pa.y;                                                                                     \
-            s_h = ph.x + ph.y;                                                                                     \
-            s_w = pw.x + pw.y;                                                                                     \
-        }                                                                                                          \
-        /* 8-lane transposed reduction of (s_a, s_h, s_w): 4 shuffles; lane 0 ends with sum(a), lane 1 sum(h), lane 2 sum(w) */ \
-        float x = (j & 1) ? s_h : s_a;                                                                             \
-        x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1);                                                 \
-        s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);                                                               \
-        float keep = (j & 2) ? s_w : x;                                                                            \
-        keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2);                                                \
-        keep += __shfl_xor_sync(0xffffffffu, keep, 4);                                                             \
-        if ((ACTIVE) && j < 3) res_base[sidx * res_stride] = keep * res_scale * (j == 0 ? 1.f : att_v);            \
-    }
+        auto flush = [&]() {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                float *gk = gp + chf[k];
+                if (inmask & 1) red_add_v4(gk, a00[k].lo.x, a00[k].lo.y, a00[k].hi.x, a00[k].hi.y);
+                if (inmask & 2) red_add_v4(gk + o01, a01[k].lo.x, a01[k].lo.y, a01[k].hi.x, a01[k].hi.y);
+                if (inmask & 4) red_add_v4(gk + o10, a10[k].lo.x, a10[k].lo.y, a10[k].hi.x, a10[k].hi.y);
+                if (inmask & 8) red_add_v4(gk + o11, a11[k].lo.x, a11[k].lo.y, a11[k].hi.x, a11[k].hi.y);
+            }
+        };
+        auto load_g = [&](const float4 &en, float4 (&g)[CH]) {
+            const float *gq = gobase + (__float_as_int(en.w) & 0xffff) * pixv;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) g[k] = ldg4(gq + chf[k]);
+        };
+        // one sample: en = its sorted entry, gr = its grad_out chunks (both already in registers)
+        auto sample = [&](const float4 &en, const float4 (&gr)[CH], bool active) {
+            float s_a = 0.f, s_h = 0.f, s_w = 0.f, att_v = 0.f;
+            int sidx = 0;
+            if (active) {
+                const int packed = __float_as_int(en.w);
+                const int cell = packed >> 20;
+                sidx = (packed & 0xffff) * qs + ((packed >> 16) & 0xf);
+                att_v = en.z;
+                if (cell != cur) {
+                    flush();
+                    cur = cell;
+                    const int cy = cell >> cs, cx = cell & ((1 << cs) - 1);  // padded coordinates of the top-left neighbour
+                    inmask = ((cy >= 1 && cx >= 1) ? 1 : 0) | ((cy >= 1 && cx <= Wv - 1) ? 2 : 0) |
+                             ((cy <= H - 1 && cx >= 1) ? 4 : 0) | ((cy <= H - 1 && cx <= Wv - 1) ? 8 : 0);
+                    gp = gbase + ((cy - 1) * Wv + cx - 1) * pixv;
+                    const unsigned vr = V_s + (unsigned)(cy * Wpb + cx * (kD * 4));
+#pragma unroll
+                    for (int k = 0; k < CH; ++k) {
+                        const unsigned a = vr + chf[k] * 4;
+                        const f4p t00 = pk(lds4(a)), t01 = pk(lds4(a + kD * 4)), t10 = pk(lds4(a + Wpb)), t11 = pk(lds4(a + Wpb + kD * 4));
+                        v00[k] = t00;
+                        dW[k] = psub(t01, t00);
+                        dH[k] = psub(t10, t00);
+                        dd[k] = psub(psub(t11, t10), dW[k]);
+                        a00[k] = a01[k] = a10[k] = a11[k] = {z2, z2};
+                    }
+                }
+                const float lh = en.x, lw = en.y;
+                const float ah = (1.f - lh) * att_v, al = lh * att_v, hw = 1.f - lw;
+                const float2 lh2 = make_float2(lh, lh), lw2 = make_float2(lw, lw);
+                const float2 w1 = make_float2(ah * hw, ah * hw), w2 = make_float2(ah * lw, ah * lw);
+                const float2 w3 = make_float2(al * hw, al * hw), w4 = make_float2(al * lw, al * lw);
+                float2 pa = z2, ph = z2, pw = z2;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const f4p g = pk(gr[k]);
+                    const float2 dh0 = __ffma2_rn(lw2, dd[k].lo, dH[k].lo), dh1 = __ffma2_rn(lw2, dd[k].hi, dH[k].hi);
+                    const float2 tp0 = __ffma2_rn(lw2, dW[k].lo, v00[k].lo), tp1 = __ffma2_rn(lw2, dW[k].hi, v00[k].hi);
+                    const float2 dw0 = __ffma2_rn(lh2, dd[k].lo, dW[k].lo), dw1 = __ffma2_rn(lh2, dd[k].hi, dW[k].hi);
+                    pa = __ffma2_rn(g.hi, __ffma2_rn(lh2, dh1, tp1), __ffma2_rn(g.lo, __ffma2_rn(lh2, dh0, tp0), pa));
+                    ph = __ffma2_rn(g.hi, dh1, __ffma2_rn(g.lo, dh0, ph));
+                    pw = __ffma2_rn(g.hi, dw1, __ffma2_rn(g.lo, dw0, pw));
+                    a00[k].lo = __ffma2_rn(w1, g.lo, a00[k].lo); a00[k].hi = __ffma2_rn(w1, g.hi, a00[k].hi);
+                    a01[k].lo = __ffma2_rn(w2, g.lo, a01[k].lo); a01[k].hi = __ffma2_rn(w2, g.hi, a01[k].hi);
+                    a10[k].lo = __ffma2_rn(w3, g.lo, a10[k].lo); a10[k].hi = __ffma2_rn(w3, g.hi, a10[k].hi);
+                    a11[k].lo = __ffma2_rn(w4, g.lo, a11[k].lo); a11[k].hi = __ffma2_rn(w4, g.hi, a11[k].hi);
+                }
+                s_a = pa.x + pa.y;
+                s_h = ph.x + ph.y;
+                s_w = pw.x + pw.y;
+            }
+            if (SPLIT == 2) {
+                s_a += __shfl_xor_sync(0xffffffffu, s_a, 1);
+                s_h += __shfl_xor_sync(0xffffffffu, s_h, 1);
+                s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);
+                if (active) {
+                    if (j == 0) *reinterpret_cast<float2 *>(res_base + sidx * 2) = make_float2(Wf * att_v * s_w, Hf * att_v * s_h);
+                    else res_base[sidx] = s_a;
+                }
+            } else {
+                // transposed reduction of (s_a, s_h, s_w): lane 0 ends with sum(a), lane 1 sum(h), lanes 2.. sum(w)
+                float x = (j & 1) ? s_h : s_a;
+                x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1);
+                s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);
+                float keep = (j & 2) ? s_w : x;
+                keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2);
+                if (SPLIT == 8) keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+                if (active && j < 3) res_base[sidx * res_stride] = keep * res_scale * (j == 0 ? 1.f : att_v);
+            }
+        };
 
         // software pipeline, unrolled by two so the prefetched registers ping-pong without moves
-        float4 enA = make_float4(0.f, 0.f, 0.f, 0.f), gA = enA, enB = enA, gB = enA;
+        float4 enA = make_float4(0.f, 0.f, 0.f, 0.f), enB = enA, gA[CH], gB[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) gA[k] = gB[k] = enA;
         if (e_lo < e_hi) {
             enA = lds4(ent_s + e_lo * 16);
-            gA = ldg4(gobase + (__float_as_int(enA.w) & 0xffff) * pixv);
+            load_g(enA, gA);
         }
         for (int it = 0; it < iters; it += 2) {
             const int e = e_lo + it;
             if (e + 1 < e_hi) {
                 enB = lds4(ent_s + (e + 1) * 16);
-                gB = ldg4(gobase + (__float_as_int(enB.w) & 0xffff) * pixv);
+                load_g(enB, gB);
             }
-            MSDA_SAMPLE(enA, gA, e < e_hi)
+            sample(enA, gA, e < e_hi);
             if (it + 1 < iters) {
                 if (e + 2 < e_hi) {
                     enA = lds4(ent_s + (e + 2) * 16);
-                    gA = ldg4(gobase + (__float_as_int(enA.w) & 0xffff) * pixv);
+                    load_g(enA, gA);
                 }
-                MSDA_SAMPLE(enB, gB, e + 1 < e_hi)
+                sample(enB, gB, e + 1 < e_hi);
             }
         }
-        if (cur >= 0) MSDA_FLUSH()
-#undef MSDA_SAMPLE
-#undef MSDA_FLUSH
+        if (cur >= 0) flush();
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+int sorted_split()
+{
+    static const int v = [] { const char *e = getenv("MSDA_SORTED_SPLIT"); const int x = e ? atoi(e) : 0; return x == 2 || x == 4 ? x : 8; }();
+    return v;
 }
 
 bool make_params(const Problem &p, SortParams &sp, size_t &smem)
@@ -380,11 +431,10 @@ cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st
         if (e != cudaSuccess) return e;
     }
     if (sp.units == 0 || p.Lq == 0) return cudaSuccess;
-    static const int threads_env = [] { const char *v = getenv("MSDA_SORTED_THREADS"); return v ? atoi(v) : 0; }();
-    const int threads = threads_env == 640 ? 640 : threads_env == 896 ? 896 : threads_env == 1024 ? 1024 : 768;
-    auto kern = p.P == 4 ? (threads == 640 ? bwd_sorted32_kernel<4, 640> : threads == 896 ? bwd_sorted32_kernel<4, 896> : threads == 1024 ? bwd_sorted32_kernel<4, 1024> : bwd_sorted32_kernel<4, 768>)
-                         : bwd_sorted32_kernel<0, 768>;
-    const int kThreads = p.P == 4 ? threads : 768;
+    const int split = sorted_split();
+    auto kern = p.P == 4 ? (split == 2 ? bwd_sorted32_kernel<4, 2> : split == 4 ? bwd_sorted32_kernel<4, 4> : bwd_sorted32_kernel<4, 8>)
+                         : (split == 2 ? bwd_sorted32_kernel<0, 2> : split == 4 ? bwd_sorted32_kernel<0, 4> : bwd_sorted32_kernel<0, 8>);
+    const int kThreads = threads_for_split(split);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)(sp.units < p.sm_count ? sp.units : p.sm_count);

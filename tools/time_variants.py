@@ -14,18 +14,19 @@ bv = sys.argv[3] if len(sys.argv) > 3 else "auto"
 dev = torch.device("cuda:0")
 shapes = torch.tensor(S4_SHAPES, dtype=torch.long, device=dev)
 start = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
-sets = [synth_inputs(torch, frames, 3 + i, torch.float32, torch.float32, dev) for i in range(4)]
+NS = int(os.environ.get('MSDA_SETS', '4'))
+sets = [synth_inputs(torch, frames, 3 + i, torch.float32, torch.float32, dev) for i in range(NS)]
 pkg.select_variant("forward", fv)
 pkg.select_variant("backward", bv)
 
 def timeit(fn, reps=100, warm=10):
     for i in range(warm):
-        fn(*sets[i % 4])
+        fn(*sets[i % NS])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(reps):
-        fn(*sets[i % 4])
+        fn(*sets[i % NS])
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
