@@ -39,11 +39,18 @@ def build_library(force=False, verbose=False):
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
+    tmp = LIB + ".tmp"
+    cmd[cmd.index(LIB)] = tmp
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libmsda_b200.so")
+    if r.returncode != 0 or not os.path.exists(tmp):
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        if os.path.exists(LIB):
+            os.remove(LIB)  # never leave a stale library behind a failed build
+        raise RuntimeError("nvcc failed building libmsda_b200.so (exit %d)" % r.returncode)
+    os.replace(tmp, LIB)
     return LIB
 
 

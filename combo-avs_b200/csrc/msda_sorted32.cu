@@ -17,6 +17,7 @@
 // are reduced over the 8 lanes with a transposed butterfly (4 shuffles instead of 9).
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "msda_kernels.h"
 
@@ -273,105 +274,130 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
                 if (inmask & 8) red_add_v4(gk + o11, a11[k].lo.x, a11[k].lo.y, a11[k].hi.x, a11[k].hi.y);
             }
         };
-        auto load_g = [&](const float4 &en, float4 (&g)[CH]) {
-            const float *gq = gobase + (__float_as_int(en.w) & 0xffff) * pixv;
+        // issue the loads of the grad_out chunks of sorted entry e2 (clamped to this group's range)
+        auto issue_g = [&](int e2, float4 (&g)[CH]) {
+            unsigned packed;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(ent_s + min(e2, e_hi - 1) * 16 + 12));
+            const float *gq = gobase + (packed & 0xffff) * pixv;
 #pragma unroll
             for (int k = 0; k < CH; ++k) g[k] = ldg4(gq + chf[k]);
         };
         // one sample: en = its sorted entry, gr = its grad_out chunks (both already in registers)
-        auto sample = [&](const float4 &en, const float4 (&gr)[CH], bool active) {
-            float s_a = 0.f, s_h = 0.f, s_w = 0.f, att_v = 0.f;
-            int sidx = 0;
-            if (active) {
-                const int packed = __float_as_int(en.w);
-                const int cell = packed >> 20;
-                sidx = (packed & 0xffff) * qs + ((packed >> 16) & 0xf);
-                att_v = en.z;
-                if (cell != cur) {
-                    flush();
-                    cur = cell;
-                    const int cy = cell >> cs, cx = cell & ((1 << cs) - 1);  // padded coordinates of the top-left neighbour
-                    inmask = ((cy >= 1 && cx >= 1) ? 1 : 0) | ((cy >= 1 && cx <= Wv - 1) ? 2 : 0) |
-                             ((cy <= H - 1 && cx >= 1) ? 4 : 0) | ((cy <= H - 1 && cx <= Wv - 1) ? 8 : 0);
-                    gp = gbase + ((cy - 1) * Wv + cx - 1) * pixv;
-                    const unsigned vr = V_s + (unsigned)(cy * Wpb + cx * (kD * 4));
-#pragma unroll
-                    for (int k = 0; k < CH; ++k) {
-                        const unsigned a = vr + chf[k] * 4;
-                        const f4p t00 = pk(lds4(a)), t01 = pk(lds4(a + kD * 4)), t10 = pk(lds4(a + Wpb)), t11 = pk(lds4(a + Wpb + kD * 4));
-                        v00[k] = t00;
-                        dW[k] = psub(t01, t00);
-                        dH[k] = psub(t10, t00);
-                        dd[k] = psub(psub(t11, t10), dW[k]);
-                        a00[k] = a01[k] = a10[k] = a11[k] = {z2, z2};
-                    }
-                }
-                const float lh = en.x, lw = en.y;
-                const float ah = (1.f - lh) * att_v, al = lh * att_v, hw = 1.f - lw;
-                const float2 lh2 = make_float2(lh, lh), lw2 = make_float2(lw, lw);
-                const float2 w1 = make_float2(ah * hw, ah * hw), w2 = make_float2(ah * lw, ah * lw);
-                const float2 w3 = make_float2(al * hw, al * hw), w4 = make_float2(al * lw, al * lw);
-                float2 pa = z2, ph = z2, pw = z2;
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const f4p g = pk(gr[k]);
-                    const float2 dh0 = __ffma2_rn(lw2, dd[k].lo, dH[k].lo), dh1 = __ffma2_rn(lw2, dd[k].hi, dH[k].hi);
-                    const float2 tp0 = __ffma2_rn(lw2, dW[k].lo, v00[k].lo), tp1 = __ffma2_rn(lw2, dW[k].hi, v00[k].hi);
-                    const float2 dw0 = __ffma2_rn(lh2, dd[k].lo, dW[k].lo), dw1 = __ffma2_rn(lh2, dd[k].hi, dW[k].hi);
-                    pa = __ffma2_rn(g.hi, __ffma2_rn(lh2, dh1, tp1), __ffma2_rn(g.lo, __ffma2_rn(lh2, dh0, tp0), pa));
-                    ph = __ffma2_rn(g.hi, dh1, __ffma2_rn(g.lo, dh0, ph));
-                    pw = __ffma2_rn(g.hi, dw1, __ffma2_rn(g.lo, dw0, pw));
-                    a00[k].lo = __ffma2_rn(w1, g.lo, a00[k].lo); a00[k].hi = __ffma2_rn(w1, g.hi, a00[k].hi);
-                    a01[k].lo = __ffma2_rn(w2, g.lo, a01[k].lo); a01[k].hi = __ffma2_rn(w2, g.hi, a01[k].hi);
-                    a10[k].lo = __ffma2_rn(w3, g.lo, a10[k].lo); a10[k].hi = __ffma2_rn(w3, g.hi, a10[k].hi);
-                    a11[k].lo = __ffma2_rn(w4, g.lo, a11[k].lo); a11[k].hi = __ffma2_rn(w4, g.hi, a11[k].hi);
-                }
-                s_a = pa.x + pa.y;
-                s_h = ph.x + ph.y;
-                s_w = pw.x + pw.y;
+#define MSDA_SAMPLE_BODY \
+            float s_a = 0.f, s_h = 0.f, s_w = 0.f, att_v = 0.f; \
+            int sidx = 0; \
+            if (active) { \
+                const int packed = __float_as_int(en.w); \
+                const int cell = packed >> 20; \
+                sidx = (packed & 0xffff) * qs + ((packed >> 16) & 0xf); \
+                att_v = en.z; \
+                if (cell != cur) { \
+                    flush(); \
+                    cur = cell; \
+                    const int cy = cell >> cs, cx = cell & ((1 << cs) - 1); \
+                    inmask = ((cy >= 1 && cx >= 1) ? 1 : 0) | ((cy >= 1 && cx <= Wv - 1) ? 2 : 0) | \
+                             ((cy <= H - 1 && cx >= 1) ? 4 : 0) | ((cy <= H - 1 && cx <= Wv - 1) ? 8 : 0); \
+                    gp = gbase + ((cy - 1) * Wv + cx - 1) * pixv; \
+                    const unsigned vr = V_s + (unsigned)(cy * Wpb + cx * (kD * 4)); \
+_Pragma("unroll") \
+                    for (int k = 0; k < CH; ++k) { \
+                        const unsigned a = vr + chf[k] * 4; \
+                        const f4p t00 = pk(lds4(a)), t01 = pk(lds4(a + kD * 4)), t10 = pk(lds4(a + Wpb)), t11 = pk(lds4(a + Wpb + kD * 4)); \
+                        v00[k] = t00; \
+                        dW[k] = psub(t01, t00); \
+                        dH[k] = psub(t10, t00); \
+                        dd[k] = psub(psub(t11, t10), dW[k]); \
+                        a00[k] = a01[k] = a10[k] = a11[k] = {z2, z2}; \
+                    } \
+                } \
+                const float lh = en.x, lw = en.y; \
+                const float ah = (1.f - lh) * att_v, al = lh * att_v, hw = 1.f - lw; \
+                const float2 lh2 = make_float2(lh, lh), lw2 = make_float2(lw, lw); \
+                const float2 w1 = make_float2(ah * hw, ah * hw), w2 = make_float2(ah * lw, ah * lw); \
+                const float2 w3 = make_float2(al * hw, al * hw), w4 = make_float2(al * lw, al * lw); \
+                float2 pa = z2, ph = z2, pw = z2; \
+_Pragma("unroll") \
+                for (int k = 0; k < CH; ++k) { \
+                    const f4p g = pk(gr[k]); \
+                    const float2 dh0 = __ffma2_rn(lw2, dd[k].lo, dH[k].lo), dh1 = __ffma2_rn(lw2, dd[k].hi, dH[k].hi); \
+                    const float2 tp0 = __ffma2_rn(lw2, dW[k].lo, v00[k].lo), tp1 = __ffma2_rn(lw2, dW[k].hi, v00[k].hi); \
+                    const float2 dw0 = __ffma2_rn(lh2, dd[k].lo, dW[k].lo), dw1 = __ffma2_rn(lh2, dd[k].hi, dW[k].hi); \
+                    pa = __ffma2_rn(g.hi, __ffma2_rn(lh2, dh1, tp1), __ffma2_rn(g.lo, __ffma2_rn(lh2, dh0, tp0), pa)); \
+                    ph = __ffma2_rn(g.hi, dh1, __ffma2_rn(g.lo, dh0, ph)); \
+                    pw = __ffma2_rn(g.hi, dw1, __ffma2_rn(g.lo, dw0, pw)); \
+                    a00[k].lo = __ffma2_rn(w1, g.lo, a00[k].lo); a00[k].hi = __ffma2_rn(w1, g.hi, a00[k].hi); \
+                    a01[k].lo = __ffma2_rn(w2, g.lo, a01[k].lo); a01[k].hi = __ffma2_rn(w2, g.hi, a01[k].hi); \
+                    a10[k].lo = __ffma2_rn(w3, g.lo, a10[k].lo); a10[k].hi = __ffma2_rn(w3, g.hi, a10[k].hi); \
+                    a11[k].lo = __ffma2_rn(w4, g.lo, a11[k].lo); a11[k].hi = __ffma2_rn(w4, g.hi, a11[k].hi); \
+                } \
+                s_a = pa.x + pa.y; \
+                s_h = ph.x + ph.y; \
+                s_w = pw.x + pw.y; \
+            } \
+            if (SPLIT == 2) { \
+                s_a += __shfl_xor_sync(0xffffffffu, s_a, 1); \
+                s_h += __shfl_xor_sync(0xffffffffu, s_h, 1); \
+                s_w += __shfl_xor_sync(0xffffffffu, s_w, 1); \
+                if (active) { \
+                    if (j == 0) *reinterpret_cast<float2 *>(res_base + sidx * 2) = make_float2(Wf * att_v * s_w, Hf * att_v * s_h); \
+                    else res_base[sidx] = s_a; \
+                } \
+            } else { \
+ \
+                float x = (j & 1) ? s_h : s_a; \
+                x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1); \
+                s_w += __shfl_xor_sync(0xffffffffu, s_w, 1); \
+                float keep = (j & 2) ? s_w : x; \
+                keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2); \
+                if (SPLIT == 8) keep += __shfl_xor_sync(0xffffffffu, keep, 4); \
+                if (active && j < 3) res_base[sidx * res_stride] = keep * res_scale * (j == 0 ? 1.f : att_v); \
             }
-            if (SPLIT == 2) {
-                s_a += __shfl_xor_sync(0xffffffffu, s_a, 1);
-                s_h += __shfl_xor_sync(0xffffffffu, s_h, 1);
-                s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);
-                if (active) {
-                    if (j == 0) *reinterpret_cast<float2 *>(res_base + sidx * 2) = make_float2(Wf * att_v * s_w, Hf * att_v * s_h);
-                    else res_base[sidx] = s_a;
-                }
-            } else {
-                // transposed reduction of (s_a, s_h, s_w): lane 0 ends with sum(a), lane 1 sum(h), lanes 2.. sum(w)
-                float x = (j & 1) ? s_h : s_a;
-                x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1);
-                s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);
-                float keep = (j & 2) ? s_w : x;
-                keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2);
-                if (SPLIT == 8) keep += __shfl_xor_sync(0xffffffffu, keep, 4);
-                if (active && j < 3) res_base[sidx * res_stride] = keep * res_scale * (j == 0 ? 1.f : att_v);
-            }
+        // nvcc 12.9 crashes on a generic lambda here, hence two plain lambdas sharing one body
+        auto sample_steady = [&](const float4 &en, const float4 (&gr)[CH]) {
+            const bool active = true;  // steady-state steps are active for every group
+            MSDA_SAMPLE_BODY
         };
+        auto sample_checked = [&](const float4 &en, const float4 (&gr)[CH], bool active) {
+            MSDA_SAMPLE_BODY
+        };
+#undef MSDA_SAMPLE_BODY
 
-        // software pipeline, unrolled by two so the prefetched registers ping-pong without moves
-        float4 enA = make_float4(0.f, 0.f, 0.f, 0.f), enB = enA, gA[CH], gB[CH];
+        // software pipeline: grad_out rows are loaded TWO samples ahead into three rotating register sets (the loop is unrolled
+        // by three so the rotation costs no moves); one sample ahead does not cover the L2 latency.  Every group owns `full`
+        // or `full`+1 entries, so the first `full` steps need no activity checks; the remainder is peeled.
+        const int full = E / kGroups, cnt = e_hi - e_lo;
+        const bool has_tail = full * kGroups != E;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 g0[CH], g1[CH], g2[CH];
 #pragma unroll
-        for (int k = 0; k < CH; ++k) gA[k] = gB[k] = enA;
-        if (e_lo < e_hi) {
-            enA = lds4(ent_s + e_lo * 16);
-            load_g(enA, gA);
+        for (int k = 0; k < CH; ++k) g0[k] = g1[k] = g2[k] = z4;
+        if (cnt > 0) {
+            issue_g(e_lo, g0);
+            issue_g(e_lo + 1, g1);
         }
-        for (int it = 0; it < iters; it += 2) {
+        int it = 0;
+        for (; it + 3 <= full; it += 3) {
             const int e = e_lo + it;
-            if (e + 1 < e_hi) {
-                enB = lds4(ent_s + (e + 1) * 16);
-                load_g(enB, gB);
-            }
-            sample(enA, gA, e < e_hi);
-            if (it + 1 < iters) {
-                if (e + 2 < e_hi) {
-                    enA = lds4(ent_s + (e + 2) * 16);
-                    load_g(enA, gA);
-                }
-                sample(enB, gB, e + 1 < e_hi);
-            }
+            issue_g(e + 2, g2);
+            sample_steady(lds4(ent_s + e * 16), g0);
+            issue_g(e + 3, g0);
+            sample_steady(lds4(ent_s + (e + 1) * 16), g1);
+            issue_g(e + 4, g1);
+            sample_steady(lds4(ent_s + (e + 2) * 16), g2);
+        }
+        const int rem = full - it + (has_tail ? 1 : 0);  // 0..3 remaining steps, the same for every group
+        if (rem >= 1) {
+            const int e = e_lo + it;
+            if (cnt > 0 && rem >= 3) issue_g(e + 2, g2);
+            sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g0, e < e_hi);
+        }
+        if (rem >= 2) {
+            const int e = e_lo + it + 1;
+            sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g1, e < e_hi);
+        }
+        if (rem >= 3) {
+            const int e = e_lo + it + 2;
+            sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g2, e < e_hi);
         }
         if (cur >= 0) flush();
     }
