@@ -36,6 +36,9 @@ struct SortParams {
     unsigned wrecip[kMaxLevels];  // ceil(2^32 / W): pixel / W == umulhi(pixel, wrecip) for pixel < 2^16
     int vrows_max;           // rows of the largest zero-padded level slab, (H+2)*(W+2)
     long long units;         // N*M*L
+    int base;                // whole units per CTA
+    int rem;                 // leftover units (units - base*grid), each cut into `parts` pieces: one piece per CTA
+    int parts;
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
@@ -109,8 +112,14 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
     const int pix = sp.M * kD;
     const int qstride = sp.M * LP;  // samples between consecutive queries of one head
 
-    const long long u_lo = sp.units * blockIdx.x / gridDim.x, u_hi = sp.units * (blockIdx.x + 1) / gridDim.x;
-    for (long long u = u_lo; u < u_hi; ++u) {
+    // schedule: CTA b runs whole units [b*base, (b+1)*base) and then, if it exists, piece b of the leftover units
+    // (leftover unit grid*base + b/parts, entry range part b%parts of `parts`): without the split the CTAs that get
+    // one unit more than the others set the kernel time (960 units over 148 CTAs: 7 vs 6.49).
+    const int n_mine = sp.base + ((int)blockIdx.x < sp.rem * sp.parts ? 1 : 0);
+    for (int ui = 0; ui < n_mine; ++ui) {
+        const bool piece = ui == sp.base;
+        const long long u = piece ? (long long)gridDim.x * sp.base + blockIdx.x / sp.parts : (long long)blockIdx.x * sp.base + ui;
+        const int part = piece ? (int)blockIdx.x % sp.parts : 0, parts = piece ? sp.parts : 1;
         const long long nm = u / sp.L;
         const int l = (int)(u - nm * sp.L);
         const long long n = nm / sp.M;
@@ -120,26 +129,6 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         const long long lvl_row = (n * sp.S + sp.start[l]) * (long long)pix + (long long)m * kD;  // pixel (0,0), channel 0
         const float *vbase = value + lvl_row;
         __syncthreads();  // previous unit is completely finished with V / ent / cell_off
-        // value level slab -> shared memory (interior by cp.async, the one-pixel border zeroed by hand)
-        for (int i = tid; i < H * W * 8; i += kThreads) {
-            const int pxl = i >> 3, c = i & 7;
-            const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
-            cp_async16(V4 + ((y + 1) * Wp + x + 1) * 8 + c, vbase + pxl * pix + c * 4);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = tid; i < Wp * 8; i += kThreads) {  // top and bottom padded rows
-                V4[i] = z;
-                V4[(H + 1) * Wp * 8 + i] = z;
-            }
-            for (int i = tid; i < H * 16; i += kThreads) {  // left and right padded columns
-                const int y = (i >> 4) + 1, side = (i >> 3) & 1, c = i & 7;
-                V4[(y * Wp + side * (W + 1)) * 8 + c] = z;
-            }
-        }
-        for (int i = tid; i <= cells; i += kThreads) cell_off[i] = 0;
-
         // ---- pass 1: cell of every sample of this level, rank inside the cell (shared-memory integer atomics) ----------
         // sample (q, p) of this (n, m, l) sits at loc2[q*qstride + p]; per-unit base pointers keep the index math 32-bit
         const long long meta0 = ((n * Lq) * sp.M + m) * (long long)LP + l * P;
@@ -162,6 +151,27 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
                 sa[r] = __ldg(att + q * qstride + p);
             }
         }
+        // (the slab copy and the zero fills below overlap the latency of the loads just issued)
+        // value level slab -> shared memory (interior by cp.async, the one-pixel border zeroed by hand)
+        for (int i = tid; i < H * W * 8; i += kThreads) {
+            const int pxl = i >> 3, c = i & 7;
+            const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
+            cp_async16(V4 + ((y + 1) * Wp + x + 1) * 8 + c, vbase + pxl * pix + c * 4);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = tid; i < Wp * 8; i += kThreads) {  // top and bottom padded rows
+                V4[i] = z;
+                V4[(H + 1) * Wp * 8 + i] = z;
+            }
+            for (int i = tid; i < H * 16; i += kThreads) {  // left and right padded columns
+                const int y = (i >> 4) + 1, side = (i >> 3) & 1, c = i & 7;
+                V4[(y * Wp + side * (W + 1)) * 8 + c] = z;
+            }
+        }
+        for (int i = tid; i <= cells; i += kThreads) cell_off[i] = 0;
+
         __syncthreads();  // counters are zero
 #pragma unroll
         for (int r = 0; r < kRounds; ++r) {
@@ -175,7 +185,7 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
                     floor_magic(w, x0);
                     const int cell = ((y0 + 1) << cs) + x0 + 1;
                     cr[r] = (cell << 16) | atomicAdd(&cell_off[cell], 1);
-                } else {  // sample outside the map: all three gradients are exactly zero (cuh:352-356)
+                } else if (part == 0) {  // sample outside the map: all three gradients are exactly zero (cuh:352-356)
                     const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
                     const int s = q * qstride + p;
                     *reinterpret_cast<float2 *>(gloc + 2 * s) = make_float2(0.f, 0.f);
@@ -240,9 +250,23 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         __syncthreads();  // sorted list complete, value slab landed
 
         // ---- walk the sorted list: every SPLIT-lane group owns a contiguous range of entries -------------------------------
-        const int E = cell_off[kMaxCells];
-        const int e_lo = (int)((long long)E * grp / kGroups), e_hi = (int)((long long)E * (grp + 1) / kGroups);
-        const int iters = (E + kGroups - 1) / kGroups;
+        const int Etot = cell_off[kMaxCells];
+        // a piece takes whole cells (the order INSIDE a cell differs between the CTAs that sort the same unit, the cell offsets do
+        // not): its range starts at the first cell whose offset reaches Etot*part/parts
+        auto cell_boundary = [&](int target) {
+            int lo = 0, hi = cells;  // first c in [0, cells] with cell_off[c] >= target (cell_off[cells] stands for Etot)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (cell_off[mid] >= target) hi = mid; else lo = mid + 1;
+            }
+            return lo < cells ? cell_off[lo] : Etot;
+        };
+        int E0 = 0, E = Etot;
+        if (parts > 1) {
+            E0 = part == 0 ? 0 : cell_boundary((int)((long long)Etot * part / parts));
+            E = (part + 1 == parts ? Etot : cell_boundary((int)((long long)Etot * (part + 1) / parts))) - E0;
+        }
+        const int e_lo = E0 + (int)((long long)E * grp / kGroups), e_hi = E0 + (int)((long long)E * (grp + 1) / kGroups);
         // grad_out row of query q: gobase + q*pix (+ chf[k]); streamed from L2, prefetched one entry ahead
         const float *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD;
         float *gbase = grad_value + lvl_row;
@@ -464,6 +488,11 @@ cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (int)(sp.units < p.sm_count ? sp.units : p.sm_count);
+    sp.base = (int)(sp.units / grid);
+    sp.rem = (int)(sp.units - (long long)sp.base * grid);
+    sp.parts = sp.rem > 0 ? grid / sp.rem : 1;
+    if (sp.parts > 4) sp.parts = 4;
+    if (sp.parts < 1) sp.parts = 1;
     kern<<<grid, kThreads, smem, st>>>((const float *)p.value, (const float *)p.loc, (const float *)p.attn,
                                                       (const float *)io.grad_out, (float *)io.grad_value, (float *)io.grad_loc,
                                                       (float *)io.grad_attn, sp);

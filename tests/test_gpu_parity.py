@@ -111,7 +111,7 @@ def test_reference_testpy_tolerances(pkg):
 
 
 # --------------------------------------------------------------------------------- every variant, S4 production shape
-@pytest.mark.parametrize("N", [1, 5, 40])
+@pytest.mark.parametrize("N", [1, 5, 20, 40])  # 20 and 40 exercise the leftover-unit splitting of sorted32 (4 and 2 pieces)
 def test_s4_shape_all_variants_fp32(pkg, N):
     d = make_inputs(N, S4_SHAPES, 8, 32, 1029, 4, seed=3 + N)
     ref = oracle_all(d)
