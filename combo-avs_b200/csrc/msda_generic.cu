@@ -166,6 +166,14 @@ cudaError_t bwd_launch(const Problem &p, const BackwardIO &io, GA *gv_acc, cudaS
 
 }  // namespace
 
+cudaError_t convert_f32_to_bf16(const float *src, void *dst, long long n, int sm_count, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    f32_to_bf16_kernel<<<sm_count * 8, 256, 0, st>>>(src, (__nv_bfloat16 *)dst, n);
+    count_launch();
+    return cudaGetLastError();
+}
+
 size_t bwd_generic_workspace(int dtype, int N, int S, int M, int D)
 {
     return dtype == 1 /*bf16*/ ? sizeof(float) * (size_t)N * S * M * D : 0;

@@ -38,6 +38,7 @@ void count_launch(int n = 1);
 cudaError_t fwd_generic(const Problem &p, void *out, cudaStream_t st);
 cudaError_t bwd_generic(const Problem &p, const BackwardIO &io, cudaStream_t st);
 size_t bwd_generic_workspace(int dtype, int N, int S, int M, int D);
+cudaError_t convert_f32_to_bf16(const float *src, void *dst, long long n, int sm_count, cudaStream_t st);
 
 // warp32: D == 32, f32, warp-cooperative gather straight from L1/L2 (msda_warp32.cu)
 bool warp32_supported(const Problem &p);

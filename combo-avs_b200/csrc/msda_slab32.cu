@@ -49,7 +49,26 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// copy value[n, :, m, :] into the padded slab (interior only; the border was zeroed once)
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+// 8 consecutive bf16 (16 bytes) -> two float4
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 &r, float4 &a, float4 &b)
+{
+    const float2 p0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
+    const float2 p1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+    const float2 p2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.z));
+    const float2 p3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.w));
+    a = make_float4(p0.x, p0.y, p1.x, p1.y);
+    b = make_float4(p2.x, p2.y, p3.x, p3.y);
+}
+
+// copy value[n, :, m, :] into the padded fp32 slab (interior only; the border was zeroed once)
 __device__ __forceinline__ void load_slab(float4 *slab, const float *__restrict__ value, const SlabParams &sp, long long nm)
 {
     const long long n = nm / sp.M;
@@ -69,6 +88,48 @@ __device__ __forceinline__ void load_slab(float4 *slab, const float *__restrict_
     cp_async_wait_all();
 }
 
+// bf16 values: rows are 64 bytes in HBM; they are widened to fp32 on the way into the slab (the gather itself is unchanged)
+__device__ __forceinline__ void load_slab(float4 *slab, const bf16 *__restrict__ value, const SlabParams &sp, long long nm)
+{
+    const long long n = nm / sp.M;
+    const int m = (int)(nm - n * sp.M);
+    const bf16 *src = value + ((n * sp.S) * sp.M + m) * kD;
+    const int pixf = sp.M * kD;
+    for (int l = 0; l < sp.L; ++l) {
+        const int W = sp.W[l], cnt = sp.H[l] * W * 4;
+        const bf16 *lsrc = src + (long long)sp.start[l] * pixf;
+        float4 *ldst = slab + (size_t)(sp.prow0[l] + (W + 2) + 1) * 8;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const int pix = i >> 2, c = i & 3;
+            const int y = (int)__umulhi((unsigned)pix, sp.wrecip[l]), x = pix - y * W;
+            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(lsrc + (long long)pix * pixf + c * 8));
+            float4 a, b;
+            bf16x8_to_f32(raw, a, b);
+            float4 *d = ldst + (size_t)(y * (W + 2) + x) * 8 + c * 2;
+            d[0] = a;
+            d[1] = b;
+        }
+    }
+    cp_async_wait_all();
+}
+
+__device__ __forceinline__ float2 to_f2(float2 v) { return v; }
+__device__ __forceinline__ float2 to_f2(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ float to_f1(float v) { return v; }
+__device__ __forceinline__ float to_f1(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ void store4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ void store4(bf16 *p, float4 v)
+{
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<unsigned *>(&lo);
+    r.y = *reinterpret_cast<unsigned *>(&hi);
+    *reinterpret_cast<uint2 *>(p) = r;
+}
+template <typename T> struct Pair;
+template <> struct Pair<float> { using type = float2; };
+template <> struct Pair<bf16> { using type = __nv_bfloat162; };
+
 // floor for |x| < 2^22 without the XU pipe: adding 1.5*2^23 with round-down leaves floor(x) in the low mantissa bits
 __device__ __forceinline__ void floor_split(float x, float &fl, int &i)
 {
@@ -81,20 +142,22 @@ __device__ __forceinline__ void floor_split(float x, float &fl, int &i)
 // per query 2*LP location floats followed by LP weights (row of 3*LP floats).  In global memory one (query, head)
 // owns 8*LP contiguous bytes of locations and 4*LP of weights at a stride of M times that, so 16-byte cp.async
 // pieces issued by consecutive lanes touch each 128-byte line once, instead of once per sample per query.
-__device__ __forceinline__ void stage_meta(float *meta, const float *__restrict__ loc, const float *__restrict__ attn,
+template <typename TM>
+__device__ __forceinline__ void stage_meta(TM *meta, const TM *__restrict__ loc, const TM *__restrict__ attn,
                                            const SlabParams &sp, int LP, long long nm, int q0, int cnt)
 {
     const long long n = nm / sp.M;
     const int m = (int)(nm - n * sp.M);
-    const int pieces = (3 * LP) >> 2, loc_pieces = LP >> 1;
+    const int pieces = (3 * LP) >> 2, loc_pieces = LP >> 1;  // pieces of 4 elements (16 bytes of fp32, 8 bytes of bf16)
     const int total = cnt * pieces;
     const long long qm0 = (n * sp.Lq + q0) * sp.M + m;
-    const float *lbase = loc + qm0 * (2 * LP), *abase = attn + qm0 * LP;
+    const TM *lbase = loc + qm0 * (2 * LP), *abase = attn + qm0 * LP;
     const int lstride = sp.M * 2 * LP, astride = sp.M * LP;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int ql = (int)__umulhi((unsigned)i, sp.precip), pc = i - ql * pieces;
-        const float *src = pc < loc_pieces ? lbase + ql * lstride + pc * 4 : abase + ql * astride + (pc - loc_pieces) * 4;
-        cp_async16(meta + ql * (3 * LP) + pc * 4, src);
+        const TM *src = pc < loc_pieces ? lbase + ql * lstride + pc * 4 : abase + ql * astride + (pc - loc_pieces) * 4;
+        if (sizeof(TM) == 4) cp_async16(meta + ql * (3 * LP) + pc * 4, src);
+        else cp_async8(meta + ql * (3 * LP) + pc * 4, src);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -112,16 +175,16 @@ __device__ __forceinline__ float4 lds4(unsigned addr)
 __device__ __forceinline__ void pin(int &x) { asm volatile("" : "+r"(x)); }
 __device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
 
-template <int P_T, bool STAGE, int SPLIT>
+template <typename TV, typename TM, int P_T, bool STAGE, int SPLIT>
 __global__ void __launch_bounds__(SPLIT == 4 ? 768 : 512, 1)
-fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc, const float *__restrict__ attn,
-                  float *__restrict__ out, const __grid_constant__ SlabParams sp)
+fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, const TM *__restrict__ attn,
+                  TV *__restrict__ out, const __grid_constant__ SlabParams sp)
 {
     constexpr int CH = 8 / SPLIT;  // 16-byte chunks (4 channels) per lane
     extern __shared__ float4 slab[];
     const int P = P_T > 0 ? P_T : sp.P;
     const int LP = sp.L * P;
-    float *meta0 = reinterpret_cast<float *>(slab + (size_t)sp.padded_rows * 8);  // two staging buffers of qpp rows
+    TM *meta0 = reinterpret_cast<TM *>(slab + (size_t)sp.padded_rows * 8);  // two staging buffers of qpp rows
     const int meta_stride = sp.qpp * 3 * LP;
     for (int i = threadIdx.x; i < sp.padded_rows * 8; i += blockDim.x) slab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long u_lo = sp.units * blockIdx.x / gridDim.x, u_hi = sp.units * (blockIdx.x + 1) / gridDim.x;
@@ -153,7 +216,7 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
     for (long long u = u_lo; u < u_hi; ++u) {
         long long nm; int q0, cnt;
         pass_range(u, nm, q0, cnt);
-        const float *meta = meta0 + ((u - u_lo) & 1) * meta_stride;
+        const TM *meta = meta0 + ((u - u_lo) & 1) * meta_stride;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();  // staged metadata visible; everyone is done with the previous pass (and the zero fill)
         if (nm != resident) {
@@ -171,8 +234,9 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
         const long long n = nm / sp.M;
         const int m = (int)(nm - n * sp.M);
         const long long qm = (n * sp.Lq + q) * sp.M + m;
-        const float2 *loc2 = STAGE ? reinterpret_cast<const float2 *>(meta + ql * 3 * LP) : reinterpret_cast<const float2 *>(loc) + qm * LP;
-        const float *att = STAGE ? meta + ql * 3 * LP + 2 * LP : attn + qm * LP;
+        using TM2 = typename Pair<TM>::type;
+        const TM2 *loc2 = STAGE ? reinterpret_cast<const TM2 *>(meta + ql * 3 * LP) : reinterpret_cast<const TM2 *>(loc) + qm * LP;
+        const TM *att = STAGE ? meta + ql * 3 * LP + 2 * LP : attn + qm * LP;
         f4p acc[CH];
 #pragma unroll
         for (int k = 0; k < CH; ++k) acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
@@ -186,8 +250,8 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
             for (int pp = 0; pp < (P_T > 0 ? P_T : 1); ++pp) {
                 for (int p = (P_T > 0 ? pp : 0); p < (P_T > 0 ? pp + 1 : P); ++p) {
                     const int s = l * P + p;
-                    const float2 xy = STAGE ? loc2[s] : __ldg(loc2 + s);
-                    float a = STAGE ? att[s] : __ldg(att + s);
+                    const float2 xy = to_f2(STAGE ? loc2[s] : __ldg(loc2 + s));
+                    float a = to_f1(STAGE ? att[s] : __ldg(att + s));
                     const float h = __fmaf_rn(xy.y, Hf, -0.5f), w = __fmaf_rn(xy.x, Wf, -0.5f);
                     const bool ok = h > -1.f && w > -1.f && h < Hf && w < Wf;
                     a = ok ? a : 0.f;
@@ -214,10 +278,9 @@ fwd_slab32_kernel(const float *__restrict__ value, const float *__restrict__ loc
                 }
             }
         }
-        float *o = out + qm * kD;
+        TV *o = out + qm * kD;
 #pragma unroll
-        for (int k = 0; k < CH; ++k)
-            *reinterpret_cast<float4 *>(o + (off[k] >> 2)) = make_float4(acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y);
+        for (int k = 0; k < CH; ++k) store4(o + (off[k] >> 2), make_float4(acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y));
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -251,7 +314,7 @@ int slab_split()
 bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &threads, int &grid, bool &stage)
 {
     const int split = slab_split();
-    if (!(p.dtype == 0 && p.loc_dtype == 0 && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
+    if (!((p.dtype == 0 || p.dtype == 1) && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
     sp.L = p.L; sp.P = p.P; sp.S = p.S; sp.M = p.M; sp.Lq = p.Lq;
     int rows = 0;
     for (int l = 0; l < p.L; ++l) {
@@ -280,10 +343,25 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
     // metadata staging (two buffers of qpp rows of 3*L*P floats) when 16-byte pieces line up and it fits
     const int LP = p.L * p.P;
     sp.precip = LP >= 4 ? (unsigned)((0x100000000ULL + (3 * LP / 4) - 1) / (3 * LP / 4)) : 0;
-    const size_t meta_bytes = 2 * (size_t)sp.qpp * 3 * LP * sizeof(float);
+    const size_t meta_bytes = 2 * (size_t)sp.qpp * 3 * LP * (p.loc_dtype == 1 ? 2 : 4);
     stage = (LP % 4 == 0) && smem_bytes + meta_bytes <= (size_t)p.smem_optin;
     if (stage) smem_bytes += meta_bytes;
     return true;
+}
+
+template <typename TV, typename TM>
+cudaError_t launch_typed(const Problem &p, void *out, cudaStream_t st, const SlabParams &sp, size_t smem, int threads, int grid, bool stage)
+{
+    const bool s4 = slab_split() == 4;
+    auto kern = p.P == 4 ? (stage ? (s4 ? fwd_slab32_kernel<TV, TM, 4, true, 4> : fwd_slab32_kernel<TV, TM, 4, true, 2>)
+                                  : (s4 ? fwd_slab32_kernel<TV, TM, 4, false, 4> : fwd_slab32_kernel<TV, TM, 4, false, 2>))
+                         : (stage ? (s4 ? fwd_slab32_kernel<TV, TM, 0, true, 4> : fwd_slab32_kernel<TV, TM, 0, true, 2>)
+                                  : (s4 ? fwd_slab32_kernel<TV, TM, 0, false, 4> : fwd_slab32_kernel<TV, TM, 0, false, 2>));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, threads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (TV *)out, sp);
+    count_launch();
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -305,16 +383,9 @@ cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st)
     bool stage;
     if (!make_params(p, sp, smem, threads, grid, stage)) return cudaErrorInvalidValue;
     if ((long long)p.N * p.M * p.Lq == 0) return cudaSuccess;
-    const bool s4 = slab_split() == 4;
-    auto kern = p.P == 4 ? (stage ? (s4 ? fwd_slab32_kernel<4, true, 4> : fwd_slab32_kernel<4, true, 2>)
-                                  : (s4 ? fwd_slab32_kernel<4, false, 4> : fwd_slab32_kernel<4, false, 2>))
-                         : (stage ? (s4 ? fwd_slab32_kernel<0, true, 4> : fwd_slab32_kernel<0, true, 2>)
-                                  : (s4 ? fwd_slab32_kernel<0, false, 4> : fwd_slab32_kernel<0, false, 2>));
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, threads, smem, st>>>((const float *)p.value, (const float *)p.loc, (const float *)p.attn, (float *)out, sp);
-    count_launch();
-    return cudaGetLastError();
+    return p.dtype == 0                    ? launch_typed<float, float>(p, out, st, sp, smem, threads, grid, stage)
+           : p.loc_dtype == 0              ? launch_typed<bf16, float>(p, out, st, sp, smem, threads, grid, stage)
+                                           : launch_typed<bf16, bf16>(p, out, st, sp, smem, threads, grid, stage);
 }
 
 }  // namespace msda

@@ -80,12 +80,32 @@ __device__ __forceinline__ float4 lds4(unsigned addr)
 
 __host__ __device__ constexpr int threads_for_split(int split) { return split == 8 ? 768 : split == 4 ? 512 : 384; }
 
+using bf16 = __nv_bfloat16;
+__device__ __forceinline__ float4 load4(const float *p) { return ldg4(p); }
+__device__ __forceinline__ float4 load4(const bf16 *p)
+{
+    const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float2 load2(const float *p) { return __ldg(reinterpret_cast<const float2 *>(p)); }
+__device__ __forceinline__ float2 load2(const bf16 *p) { return __bfloat1622float2(__ldg(reinterpret_cast<const __nv_bfloat162 *>(p))); }
+__device__ __forceinline__ float load1(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float load1(const bf16 *p) { return __bfloat162float(__ldg(p)); }
+__device__ __forceinline__ void store1(float *p, float v) { *p = v; }
+__device__ __forceinline__ void store1(bf16 *p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2(bf16 *p, float a, float b) { *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(a, b); }
+
 // SPLIT lanes share one sample; each lane owns CH = 8/SPLIT chunks of 4 channels.
-template <int P_T, int SPLIT>
+// TV: value / grad_out element type (float or bf16; grad_value always accumulates in fp32: for bf16 into a workspace that a
+// second kernel narrows).  TM: element type of sampling locations, attention weights and their gradients.
+template <typename TV, typename TM, int P_T, int SPLIT>
 __global__ void __launch_bounds__(threads_for_split(SPLIT), 1)
-bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ loc, const float *__restrict__ attn,
-                    const float *__restrict__ grad_out, float *__restrict__ grad_value, float *__restrict__ grad_loc,
-                    float *__restrict__ grad_attn, const __grid_constant__ SortParams sp)
+bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, const TM *__restrict__ attn,
+                    const TV *__restrict__ grad_out, float *__restrict__ grad_value, TM *__restrict__ grad_loc,
+                    TM *__restrict__ grad_attn, const __grid_constant__ SortParams sp)
 {
     constexpr int kThreads = threads_for_split(SPLIT), CH = 8 / SPLIT;
     constexpr int kGroups = kThreads / SPLIT, kRounds = (kMaxSamples + kThreads - 1) / kThreads;
@@ -127,15 +147,15 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         const int H = sp.H[l], W = sp.W[l], cs = sp.cshift[l], cells = (H + 1) << cs, Wp = W + 2;
         const float Hf = (float)H, Wf = (float)W;
         const long long lvl_row = (n * sp.S + sp.start[l]) * (long long)pix + (long long)m * kD;  // pixel (0,0), channel 0
-        const float *vbase = value + lvl_row;
+        const TV *vbase = value + lvl_row;
         __syncthreads();  // previous unit is completely finished with V / ent / cell_off
         // ---- pass 1: cell of every sample of this level, rank inside the cell (shared-memory integer atomics) ----------
         // sample (q, p) of this (n, m, l) sits at loc2[q*qstride + p]; per-unit base pointers keep the index math 32-bit
         const long long meta0 = ((n * Lq) * sp.M + m) * (long long)LP + l * P;
-        const float2 *loc2 = reinterpret_cast<const float2 *>(loc) + meta0;
-        const float *att = attn + meta0;
-        float *gloc = grad_loc + 2 * meta0;
-        float *gatt = grad_attn + meta0;
+        const TM *locb = loc + 2 * meta0;
+        const TM *att = attn + meta0;
+        TM *gloc = grad_loc + 2 * meta0;
+        TM *gatt = grad_attn + meta0;
         float sx[kRounds], sy[kRounds], sa[kRounds];
         int cr[kRounds];  // cell << 16 | rank, or -1
 #pragma unroll
@@ -145,18 +165,26 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
             sa[r] = 0.f;
             if (i < EP) {
                 const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
-                const float2 xy = __ldg(loc2 + q * qstride + p);
+                const float2 xy = load2(locb + 2 * (q * qstride + p));
                 sx[r] = xy.x;
                 sy[r] = xy.y;
-                sa[r] = __ldg(att + q * qstride + p);
+                sa[r] = load1(att + q * qstride + p);
             }
         }
         // (the slab copy and the zero fills below overlap the latency of the loads just issued)
         // value level slab -> shared memory (interior by cp.async, the one-pixel border zeroed by hand)
-        for (int i = tid; i < H * W * 8; i += kThreads) {
-            const int pxl = i >> 3, c = i & 7;
-            const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
-            cp_async16(V4 + ((y + 1) * Wp + x + 1) * 8 + c, vbase + pxl * pix + c * 4);
+        if (sizeof(TV) == 4) {
+            for (int i = tid; i < H * W * 8; i += kThreads) {
+                const int pxl = i >> 3, c = i & 7;
+                const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
+                cp_async16(V4 + ((y + 1) * Wp + x + 1) * 8 + c, vbase + pxl * pix + c * 4);
+            }
+        } else {  // bf16 rows (64 bytes) are widened to fp32 on the way in
+            for (int i = tid; i < H * W * 8; i += kThreads) {
+                const int pxl = i >> 3, c = i & 7;
+                const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
+                V4[((y + 1) * Wp + x + 1) * 8 + c] = load4(vbase + pxl * pix + c * 4);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         {
@@ -188,8 +216,8 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
                 } else if (part == 0) {  // sample outside the map: all three gradients are exactly zero (cuh:352-356)
                     const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
                     const int s = q * qstride + p;
-                    *reinterpret_cast<float2 *>(gloc + 2 * s) = make_float2(0.f, 0.f);
-                    gatt[s] = 0.f;
+                    store2(gloc + 2 * s, 0.f, 0.f);
+                    store1(gatt + s, 0.f);
                 }
             }
         }
@@ -268,7 +296,7 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         }
         const int e_lo = E0 + (int)((long long)E * grp / kGroups), e_hi = E0 + (int)((long long)E * (grp + 1) / kGroups);
         // grad_out row of query q: gobase + q*pix (+ chf[k]); streamed from L2, prefetched one entry ahead
-        const float *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD;
+        const TV *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD;
         float *gbase = grad_value + lvl_row;
         const int o01 = pix, o10 = W * pix, o11 = (W + 1) * pix;
         unsigned V_s = (unsigned)__cvta_generic_to_shared(V4);
@@ -276,7 +304,7 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         int qs = qstride, pixv = pix, Wv = W, Wpb = Wp * (kD * 4);
         pin(qs); pin(pixv); pin(Wv); pin(Wpb);
         // result stores: SPLIT >= 4: lane 0 grad_attn, lane 1 grad_loc.y, lane 2 grad_loc.x; SPLIT == 2: lane 0 grad_loc (float2), lane 1 grad_attn
-        float *res_base = SPLIT >= 4 ? (j == 0 ? gatt : gloc + (j == 1 ? 1 : 0)) : (j == 0 ? gloc : gatt);
+        TM *res_base = SPLIT >= 4 ? (j == 0 ? gatt : gloc + (j == 1 ? 1 : 0)) : (j == 0 ? gloc : gatt);
         int res_stride = SPLIT >= 4 ? (j == 0 ? 1 : 2) : (j == 0 ? 2 : 1);
         float res_scale = j == 0 ? 1.f : (j == 1 ? Hf : Wf);
         pin(res_base); pin(res_stride); pin(res_scale); pin(gobase); pin(gbase);
@@ -302,9 +330,9 @@ bwd_sorted32_kernel(const float *__restrict__ value, const float *__restrict__ l
         auto issue_g = [&](int e2, float4 (&g)[CH]) {
             unsigned packed;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(ent_s + min(e2, e_hi - 1) * 16 + 12));
-            const float *gq = gobase + (packed & 0xffff) * pixv;
+            const TV *gq = gobase + (packed & 0xffff) * pixv;
 #pragma unroll
-            for (int k = 0; k < CH; ++k) g[k] = ldg4(gq + chf[k]);
+            for (int k = 0; k < CH; ++k) g[k] = load4(gq + chf[k]);
         };
         // one sample: en = its sorted entry, gr = its grad_out chunks (both already in registers)
 #define MSDA_SAMPLE_BODY \
@@ -363,8 +391,8 @@ _Pragma("unroll") \
                 s_h += __shfl_xor_sync(0xffffffffu, s_h, 1); \
                 s_w += __shfl_xor_sync(0xffffffffu, s_w, 1); \
                 if (active) { \
-                    if (j == 0) *reinterpret_cast<float2 *>(res_base + sidx * 2) = make_float2(Wf * att_v * s_w, Hf * att_v * s_h); \
-                    else res_base[sidx] = s_a; \
+                    if (j == 0) store2(res_base + sidx * 2, Wf * att_v * s_w, Hf * att_v * s_h); \
+                    else store1(res_base + sidx, s_a); \
                 } \
             } else { \
  \
@@ -374,7 +402,7 @@ _Pragma("unroll") \
                 float keep = (j & 2) ? s_w : x; \
                 keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2); \
                 if (SPLIT == 8) keep += __shfl_xor_sync(0xffffffffu, keep, 4); \
-                if (active && j < 3) res_base[sidx * res_stride] = keep * res_scale * (j == 0 ? 1.f : att_v); \
+                if (active && j < 3) store1(res_base + sidx * res_stride, keep * res_scale * (j == 0 ? 1.f : att_v)); \
             }
         // nvcc 12.9 crashes on a generic lambda here, hence two plain lambdas sharing one body
         auto sample_steady = [&](const float4 &en, const float4 (&gr)[CH]) {
@@ -436,7 +464,7 @@ int sorted_split()
 
 bool make_params(const Problem &p, SortParams &sp, size_t &smem)
 {
-    if (!(p.dtype == 0 && p.loc_dtype == 0 && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
+    if (!((p.dtype == 0 || p.dtype == 1) && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
     if (p.Lq < 1 || p.Lq > 65535 || p.P > 16 || (long long)p.Lq * p.P > kMaxSamples) return false;
     sp.L = p.L; sp.P = p.P; sp.S = p.S; sp.M = p.M; sp.Lq = p.Lq;
     for (int l = 0; l < p.L; ++l) {
@@ -461,6 +489,27 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem)
     return smem <= (size_t)p.smem_optin;
 }
 
+template <typename TV, typename TM>
+cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc, SortParams &sp, size_t smem, cudaStream_t st)
+{
+    const int split = sorted_split();
+    auto kern = p.P == 4 ? (split == 2 ? bwd_sorted32_kernel<TV, TM, 4, 2> : split == 4 ? bwd_sorted32_kernel<TV, TM, 4, 4> : bwd_sorted32_kernel<TV, TM, 4, 8>)
+                         : (split == 2 ? bwd_sorted32_kernel<TV, TM, 0, 2> : split == 4 ? bwd_sorted32_kernel<TV, TM, 0, 4> : bwd_sorted32_kernel<TV, TM, 0, 8>);
+    const int kThreads = threads_for_split(split);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (int)(sp.units < p.sm_count ? sp.units : p.sm_count);
+    sp.base = (int)(sp.units / grid);
+    sp.rem = (int)(sp.units - (long long)sp.base * grid);
+    sp.parts = sp.rem > 0 ? grid / sp.rem : 1;
+    if (sp.parts > 4) sp.parts = 4;
+    if (sp.parts < 1) sp.parts = 1;
+    kern<<<grid, kThreads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (const TV *)io.grad_out, gv_acc,
+                                       (TM *)io.grad_loc, (TM *)io.grad_attn, sp);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 bool sorted32_supported(const Problem &p)
@@ -476,28 +525,18 @@ cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st
     size_t smem;
     if (!make_params(p, sp, smem)) return cudaErrorInvalidValue;
     const long long n_val = (long long)p.N * p.S * p.M * p.D;
+    float *acc = p.dtype == 0 ? (float *)io.grad_value : (float *)io.workspace;  // bf16: fp32 accumulation in the workspace
     if (n_val > 0) {
-        cudaError_t e = cudaMemsetAsync(io.grad_value, 0, sizeof(float) * (size_t)n_val, st);
+        cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)n_val, st);
         if (e != cudaSuccess) return e;
     }
     if (sp.units == 0 || p.Lq == 0) return cudaSuccess;
-    const int split = sorted_split();
-    auto kern = p.P == 4 ? (split == 2 ? bwd_sorted32_kernel<4, 2> : split == 4 ? bwd_sorted32_kernel<4, 4> : bwd_sorted32_kernel<4, 8>)
-                         : (split == 2 ? bwd_sorted32_kernel<0, 2> : split == 4 ? bwd_sorted32_kernel<0, 4> : bwd_sorted32_kernel<0, 8>);
-    const int kThreads = threads_for_split(split);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = p.dtype == 0      ? launch_sorted<float, float>(p, io, acc, sp, smem, st)
+                    : p.loc_dtype == 0 ? launch_sorted<bf16, float>(p, io, acc, sp, smem, st)
+                                       : launch_sorted<bf16, bf16>(p, io, acc, sp, smem, st);
     if (e != cudaSuccess) return e;
-    const int grid = (int)(sp.units < p.sm_count ? sp.units : p.sm_count);
-    sp.base = (int)(sp.units / grid);
-    sp.rem = (int)(sp.units - (long long)sp.base * grid);
-    sp.parts = sp.rem > 0 ? grid / sp.rem : 1;
-    if (sp.parts > 4) sp.parts = 4;
-    if (sp.parts < 1) sp.parts = 1;
-    kern<<<grid, kThreads, smem, st>>>((const float *)p.value, (const float *)p.loc, (const float *)p.attn,
-                                                      (const float *)io.grad_out, (float *)io.grad_value, (float *)io.grad_loc,
-                                                      (float *)io.grad_attn, sp);
-    count_launch();
-    return cudaGetLastError();
+    if (p.dtype == 1) return convert_f32_to_bf16(acc, io.grad_value, n_val, p.sm_count, st);
+    return cudaSuccess;
 }
 
 }  // namespace msda
