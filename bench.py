@@ -54,6 +54,15 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_traffic(variant):
+    """DRAM bytes per launch of a kernel variant from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(variant)
+    except Exception:
+        return None
+
+
 def synth_inputs(torch, n_frames, seed, dtype, loc_dtype, device, pin=False):
     g = torch.Generator().manual_seed(seed)
     value = torch.rand(n_frames, S, M, D, generator=g) * 0.01
@@ -267,7 +276,8 @@ def run_ours(args):
     dom = ("backward", bytes_b, us_b) if us_b >= us_f else ("forward", bytes_f, us_f)
     achieved = dom[1] / (dom[2] * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "%s (%s)" % (dom[0], pkg.last_variant(dom[0])), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": (load_traffic(pkg.last_variant(dom[0])) or {}).get("dram_bytes_per_launch") if args.dtype == "fp32" and nF == 40 else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom[1], "us_per_launch": dom[2],
                 "fwd": {"us": us_f, "bytes": bytes_f, "GBps": bytes_f / us_f / 1e3, "frac": bytes_f / us_f / 1e3 / peak, "variant": pkg.last_variant("forward")},
                 "bwd": {"us": us_b, "bytes": bytes_b, "GBps": bytes_b / us_b / 1e3, "frac": bytes_b / us_b / 1e3 / peak, "variant": pkg.last_variant("backward")},

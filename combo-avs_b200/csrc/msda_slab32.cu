@@ -84,8 +84,8 @@ __device__ __forceinline__ void load_slab(float4 *slab, const float *__restrict_
             const int y = (int)__umulhi((unsigned)pix, sp.wrecip[l]), x = pix - y * W;
             cp_async16(ldst + (size_t)(y * (W + 2) + x) * 8 + c, lsrc + (long long)pix * pixf + c * 4);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per level: the gather of level l waits only for it
     }
-    cp_async_wait_all();
 }
 
 // bf16 values: rows are 64 bytes in HBM; they are widened to fp32 on the way into the slab (the gather itself is unchanged)
@@ -109,8 +109,8 @@ __device__ __forceinline__ void load_slab(float4 *slab, const bf16 *__restrict__
             d[0] = a;
             d[1] = b;
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // (empty group: keeps the group arithmetic identical to the fp32 path)
     }
-    cp_async_wait_all();
 }
 
 __device__ __forceinline__ float2 to_f2(float2 v) { return v; }
@@ -129,6 +129,18 @@ __device__ __forceinline__ void store4(bf16 *p, float4 v)
 template <typename T> struct Pair;
 template <> struct Pair<float> { using type = float2; };
 template <> struct Pair<bf16> { using type = __nv_bfloat162; };
+
+// wait until at most n cp.async groups of this thread are pending (n is small; the instruction needs an immediate)
+__device__ __forceinline__ void cp_async_wait_pending(int n)
+{
+    switch (n) {
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    }
+}
 
 // floor for |x| < 2^22 without the XU pipe: adding 1.5*2^23 with round-down leaves floor(x) in the low mantissa bits
 __device__ __forceinline__ void floor_split(float x, float &fl, int &i)
@@ -186,7 +198,19 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
     const int LP = sp.L * P;
     TM *meta0 = reinterpret_cast<TM *>(slab + (size_t)sp.padded_rows * 8);  // two staging buffers of qpp rows
     const int meta_stride = sp.qpp * 3 * LP;
-    for (int i = threadIdx.x; i < sp.padded_rows * 8; i += blockDim.x) slab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < sp.L; ++l) {  // zero the one-pixel border of every level once; slab loads only ever write interiors
+        const int H = sp.H[l], Wp = sp.W[l] + 2;
+        float4 *lv = slab + (size_t)sp.prow0[l] * 8;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = threadIdx.x; i < Wp * 8; i += blockDim.x) {
+            lv[i] = z;
+            lv[(H + 1) * Wp * 8 + i] = z;
+        }
+        for (int i = threadIdx.x; i < H * 16; i += blockDim.x) {
+            const int y = (i >> 4) + 1, side = (i >> 3) & 1, c = i & 7;
+            lv[(y * Wp + side * (Wp - 1)) * 8 + c] = z;
+        }
+    }
     const long long u_lo = sp.units * blockIdx.x / gridDim.x, u_hi = sp.units * (blockIdx.x + 1) / gridDim.x;
     int ql = threadIdx.x / SPLIT;
     const int part = threadIdx.x % SPLIT;
@@ -219,17 +243,21 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
         const TM *meta = meta0 + ((u - u_lo) & 1) * meta_stride;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();  // staged metadata visible; everyone is done with the previous pass (and the zero fill)
-        if (nm != resident) {
+        const bool fresh = nm != resident;  // a new slab: its levels arrive as separate cp.async groups
+        if (fresh) {
             load_slab(slab, value, sp, nm);
-            __syncthreads();
             resident = nm;
         }
-        if (STAGE && u + 1 < u_hi) {  // prefetch the next pass's metadata while this one computes
-            long long nm2; int q02, cnt2;
-            pass_range(u + 1, nm2, q02, cnt2);
-            stage_meta(meta0 + ((u + 1 - u_lo) & 1) * meta_stride, loc, attn, sp, LP, nm2, q02, cnt2);
+        if (STAGE) {  // prefetch the next pass's metadata while this one computes (always one group, possibly empty)
+            if (u + 1 < u_hi) {
+                long long nm2; int q02, cnt2;
+                pass_range(u + 1, nm2, q02, cnt2);
+                stage_meta(meta0 + ((u + 1 - u_lo) & 1) * meta_stride, loc, attn, sp, LP, nm2, q02, cnt2);
+            } else {
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
         }
-        if (ql >= cnt) continue;
+        const bool live = ql < cnt;
         const int q = q0 + ql;
         const long long n = nm / sp.M;
         const int m = (int)(nm - n * sp.M);
@@ -241,6 +269,11 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
 #pragma unroll
         for (int k = 0; k < CH; ++k) acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
         for (int l = 0; l < sp.L; ++l) {
+            if (fresh) {  // level l of the new slab must have landed (levels after it and the metadata group may still be in flight)
+                cp_async_wait_pending(sp.L - 1 - l + (STAGE ? 1 : 0));
+                __syncthreads();
+            }
+            if (!live) continue;
             const float Hf = (float)sp.H[l], Wf = (float)sp.W[l];
             const float hmax = sp.hmax[l], wmax = sp.wmax[l];
             const int pitch = sp.W[l] + 2;
@@ -278,6 +311,7 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
                 }
             }
         }
+        if (!live) continue;
         TV *o = out + qm * kD;
 #pragma unroll
         for (int k = 0; k < CH; ++k) store4(o + (off[k] >> 2), make_float4(acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y));
