@@ -21,9 +21,9 @@ thread_local char t_error[512] = "";
 std::atomic<const char *> g_last_variant[2] = {{"none"}, {"none"}};  // process-wide: backward runs on the autograd thread
 
 enum FwdVariant { kFwdAuto = 0, kFwdGeneric, kFwdWarp32, kFwdSlab32, kFwdCount };
-enum BwdVariant { kBwdAuto = 0, kBwdGeneric, kBwdWarp32, kBwdSorted32, kBwdCount };
+enum BwdVariant { kBwdAuto = 0, kBwdGeneric, kBwdWarp32, kBwdSorted32, kBwdPipe32, kBwdCount };
 const char *const kFwdNames[kFwdCount] = {"auto", "generic", "warp32", "slab32"};
-const char *const kBwdNames[kBwdCount] = {"auto", "generic", "warp32", "sorted32"};
+const char *const kBwdNames[kBwdCount] = {"auto", "generic", "warp32", "sorted32", "pipe32"};
 std::atomic<int> g_forced[2] = {{0}, {0}};
 
 int fail(int code, const char *fmt, ...)
@@ -153,7 +153,7 @@ uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_rela
 
 const char *msda_variant_names(int pass_)
 {
-    return pass_ == 0 ? "auto,generic,warp32,slab32" : "auto,generic,warp32,sorted32";
+    return pass_ == 0 ? "auto,generic,warp32,slab32" : "auto,generic,warp32,sorted32,pipe32";
 }
 
 const char *msda_last_variant(int pass_) { return (pass_ == 0 || pass_ == 1) ? g_last_variant[pass_].load() : "none"; }
@@ -212,9 +212,10 @@ int msda_forward(int dtype, int loc_dtype, const void *value, const int64_t *spa
 
 size_t msda_backward_workspace_bytes(int dtype, int loc_dtype, int N, int S, int M, int D, int L, int Lq, int P)
 {
-    (void)loc_dtype; (void)L; (void)Lq; (void)P;
+    (void)loc_dtype; (void)L;
     if (N <= 0 || S <= 0 || M <= 0 || D <= 0) return 0;
-    return bwd_generic_workspace(dtype, N, S, M, D);
+    const size_t a = bwd_generic_workspace(dtype, N, S, M, D), b = bwd_pipe32_workspace(dtype, D, Lq, P);
+    return a > b ? a : b;
 }
 
 int msda_backward(int dtype, int loc_dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
@@ -248,9 +249,14 @@ int msda_backward(int dtype, int loc_dtype, const void *value, const int64_t *sp
 
     BackwardIO io{grad_output, grad_value, grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes};
     int v = g_forced[1].load();
-    if (v == kBwdAuto) v = sorted32_supported(p) ? kBwdSorted32 : warp32_supported(p) ? kBwdWarp32 : kBwdGeneric;
+    if (v == kBwdAuto) v = pipe32_supported(p) ? kBwdPipe32 : sorted32_supported(p) ? kBwdSorted32 : warp32_supported(p) ? kBwdWarp32 : kBwdGeneric;
     if (S == 0) v = kBwdGeneric;
     switch (v) {
+    case kBwdPipe32:
+        if (!pipe32_supported(p))
+            return fail(MSDA_ERR_VARIANT, "backward variant pipe32 needs f32, D=32, host geometry, Lq*P <= 4608, (H+1)*(W+1) <= 1024 per level");
+        e = bwd_pipe32(p, io, st);
+        break;
     case kBwdSorted32:
         if (!sorted32_supported(p))
             return fail(MSDA_ERR_VARIANT, "backward variant sorted32 needs f32, D=32, host geometry, Lq*P <= 4608, (H+1)*(W+1) <= 1024 per level");

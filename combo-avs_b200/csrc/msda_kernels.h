@@ -53,4 +53,9 @@ cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st);
 bool sorted32_supported(const Problem &p);
 cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st);
 
+// pipe32: sorted32's design with the sort of unit u+1 overlapped with the walk of unit u (msda_pipe32.cu)
+bool pipe32_supported(const Problem &p);
+size_t bwd_pipe32_workspace(int dtype, int D, int Lq, int P);
+cudaError_t bwd_pipe32(const Problem &p, const BackwardIO &io, cudaStream_t st);
+
 }  // namespace msda

@@ -87,7 +87,8 @@ int msda_backward(int dtype, int loc_dtype,
                   void *workspace, size_t workspace_bytes,
                   int device, void *stream);
 
-/* Scratch bytes msda_backward needs for this problem (0 for most float32 paths). */
+/* Scratch bytes msda_backward needs for this problem: the fp32 accumulator of grad_value for bf16 values, the sorted
+ * sample lists of the pipelined D=32 float32 backward (about 25 MB for the S4 shape, independent of N), else 0. */
 size_t msda_backward_workspace_bytes(int dtype, int loc_dtype, int N, int S, int M, int D, int L, int Lq, int P);
 
 /*
