@@ -214,7 +214,8 @@ size_t msda_backward_workspace_bytes(int dtype, int loc_dtype, int N, int S, int
 {
     (void)loc_dtype; (void)L;
     if (N <= 0 || S <= 0 || M <= 0 || D <= 0) return 0;
-    const size_t a = bwd_generic_workspace(dtype, N, S, M, D), b = bwd_pipe32_workspace(dtype, D, Lq, P);
+    // the experimental pipe32 backward keeps its sorted sample lists in scratch; it only runs when it is forced
+    const size_t a = bwd_generic_workspace(dtype, N, S, M, D), b = g_forced[1].load() == kBwdPipe32 ? bwd_pipe32_workspace(dtype, D, Lq, P) : 0;
     return a > b ? a : b;
 }
 
@@ -249,7 +250,7 @@ int msda_backward(int dtype, int loc_dtype, const void *value, const int64_t *sp
 
     BackwardIO io{grad_output, grad_value, grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes};
     int v = g_forced[1].load();
-    if (v == kBwdAuto) v = pipe32_supported(p) ? kBwdPipe32 : sorted32_supported(p) ? kBwdSorted32 : warp32_supported(p) ? kBwdWarp32 : kBwdGeneric;
+    if (v == kBwdAuto) v = sorted32_supported(p) ? kBwdSorted32 : warp32_supported(p) ? kBwdWarp32 : kBwdGeneric;
     if (S == 0) v = kBwdGeneric;
     switch (v) {
     case kBwdPipe32:

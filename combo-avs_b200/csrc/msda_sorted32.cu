@@ -13,6 +13,12 @@
 //   - per sample only ONE 128-byte row is read: its grad_output row, streamed from L2 and prefetched one sample ahead
 //     (the value level slab, zero-padded, sits in shared memory so a cell switch costs 8 LDS, not 8 L2 round trips),
 //   - grad_sampling_loc / grad_attn_weight are 4-lane shuffle reductions and plain stores.
+// MODE bit 0 (default on): the grad_out chunks do not travel through prefetch registers -- ptxas puts all of those LDGs on
+// one scoreboard, so the first use of any of them waits for ALL of them, including the one issued a few instructions
+// earlier (20 % long-scoreboard stalls in profiles/r01p) -- but through a private shared-memory slot per lane, filled by
+// cp.async two steps ahead and read back after cp.async.wait_group 2: a counted, in-order wait.
+// MODE bit 1: the reduction + stores of sample i are deferred into the basic block of sample i+1.
+// Every unit also prefetches the NEXT unit's locations, weights and value rows (and the next slab's grad_out rows) into L2.
 // A lane group is 8 lanes x 4 channels (one 128-byte row per LDS.128 phase: conflict-free); the three per-sample sums
 // are reduced over the 8 lanes with a transposed butterfly (4 shuffles instead of 9).
 #include <cmath>
@@ -39,6 +45,7 @@ struct SortParams {
     int base;                // whole units per CTA
     int rem;                 // leftover units (units - base*grid), each cut into `parts` pieces: one piece per CTA
     int parts;
+    int prefetch;            // L2-prefetch the next unit's inputs during the walk
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
@@ -101,7 +108,7 @@ __device__ __forceinline__ void store2(bf16 *p, float a, float b) { *reinterpret
 // SPLIT lanes share one sample; each lane owns CH = 8/SPLIT chunks of 4 channels.
 // TV: value / grad_out element type (float or bf16; grad_value always accumulates in fp32: for bf16 into a workspace that a
 // second kernel narrows).  TM: element type of sampling locations, attention weights and their gradients.
-template <typename TV, typename TM, int P_T, int SPLIT>
+template <typename TV, typename TM, int P_T, int SPLIT, int MODE>
 __global__ void __launch_bounds__(threads_for_split(SPLIT), 1)
 bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, const TM *__restrict__ attn,
                     const TV *__restrict__ grad_out, float *__restrict__ grad_value, TM *__restrict__ grad_loc,
@@ -116,6 +123,10 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
     float4 *ent = smem4 + (size_t)sp.vrows_max * 8;       // sorted samples: {lh, lw, attn, cell<<20 | p<<16 | q}
     int *cell_off = reinterpret_cast<int *>(ent + EP);    // kMaxCells + 1 counters -> exclusive offsets
     int *warp_tot = cell_off + kMaxCells + 8;
+    constexpr bool GRING = (MODE & 1) != 0, DEFER = (MODE & 2) != 0;
+    // GRING: slot (stage, k) of thread t at gring + ((stage*CH + k) * kThreads + t) * 16 bytes, three stages
+    unsigned gslot_s = (unsigned)__cvta_generic_to_shared(warp_tot + 32) + threadIdx.x * 16;
+    pin(gslot_s);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int grp = tid / SPLIT;
     int j = tid % SPLIT;                                  // lane j of its sample group
@@ -277,6 +288,26 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();  // sorted list complete, value slab landed
 
+        // ---- L2 prefetch of the next whole unit of this CTA: its locations / weights, its value rows and, when it starts a new
+        // (frame, head) slab, its grad_out rows -- so that the next sort and walk find them in L2 instead of paying HBM latency
+        if (sp.prefetch && ui + 1 < sp.base) {
+            const long long u2 = u + 1, nm2 = u2 / sp.L;
+            const int l2 = (int)(u2 - nm2 * sp.L);
+            const long long n2 = nm2 / sp.M;
+            const int m2 = (int)(nm2 - n2 * sp.M);
+            const long long meta2 = ((n2 * Lq) * sp.M + m2) * (long long)LP + l2 * P;
+            const TM *loc2 = loc + 2 * meta2, *att2 = attn + meta2;
+            for (int q = tid; q < Lq; q += kThreads) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(loc2 + 2 * (q * qstride)));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(att2 + q * qstride));
+            }
+            const TV *v2 = value + (n2 * sp.S + sp.start[l2]) * (long long)pix + (long long)m2 * kD;
+            for (int i = tid; i < sp.H[l2] * sp.W[l2]; i += kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(v2 + i * pix));
+            if (l2 == 0) {
+                const TV *g2p = grad_out + (n2 * Lq * sp.M + m2) * (long long)kD;
+                for (int q = tid; q < Lq; q += kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(g2p + q * pix));
+            }
+        }
         // ---- walk the sorted list: every SPLIT-lane group owns a contiguous range of entries -------------------------------
         const int Etot = cell_off[kMaxCells];
         // a piece takes whole cells (the order INSIDE a cell differs between the CTAs that sort the same unit, the cell offsets do
@@ -326,13 +357,55 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                 if (inmask & 8) red_add_v4(gk + o11, a11[k].lo.x, a11[k].lo.y, a11[k].hi.x, a11[k].hi.y);
             }
         };
-        // issue the loads of the grad_out chunks of sorted entry e2 (clamped to this group's range)
-        auto issue_g = [&](int e2, float4 (&g)[CH]) {
+        // start the loads of the grad_out chunks of sorted entry e2 (clamped to this group's range): into the lane's shared-memory
+        // slot `si` (GRING; one cp.async group per call) or into the register set g
+        auto issue_g = [&](int e2, int si, float4 (&g)[CH]) {
             unsigned packed;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(ent_s + min(e2, e_hi - 1) * 16 + 12));
             const TV *gq = gobase + (packed & 0xffff) * pixv;
+            if (GRING) {
 #pragma unroll
-            for (int k = 0; k < CH; ++k) g[k] = load4(gq + chf[k]);
+                for (int k = 0; k < CH; ++k) {
+                    const unsigned slot = gslot_s + (unsigned)((si * CH + k) * kThreads) * 16;
+                    if (sizeof(TV) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(gq + chf[k]) : "memory");
+                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot), "l"(gq + chf[k]) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) g[k] = load4(gq + chf[k]);
+            }
+        };
+        // GRING: wait for the copy into slot `si` (all but the two newest groups, or everything when `drain`) and read it back
+        auto fetch_g = [&](int si, bool drain, float4 (&g)[CH]) {
+            if (!GRING) return;
+            if (drain) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            else asm volatile("cp.async.wait_group 2;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const unsigned slot = gslot_s + (unsigned)((si * CH + k) * kThreads) * 16;
+                if (sizeof(TV) == 4) {
+                    g[k] = lds4(slot);
+                } else {
+                    uint2 r;
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(slot));
+                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
+                    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
+                    g[k] = make_float4(a.x, a.y, b.x, b.y);
+                }
+            }
+        };
+        // deferred tail of the previous sample (DEFER): its three lane-partial sums, weight and result index
+        float d_a = 0.f, d_h = 0.f, d_w = 0.f, d_att = 0.f;
+        int d_idx = -1;
+        auto finish = [&](float s_a, float s_h, float s_w, float att_v, int sidx) {  // SPLIT >= 4: transposed butterfly + stores
+            float x = (j & 1) ? s_h : s_a;
+            x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1);
+            s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);
+            float keep = (j & 2) ? s_w : x;
+            keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2);
+            if (SPLIT == 8) keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+            if (sidx >= 0 && j < 3) store1(res_base + sidx * res_stride, keep * res_scale * (j == 0 ? 1.f : att_v));
         };
         // one sample: en = its sorted entry, gr = its grad_out chunks (both already in registers)
 #define MSDA_SAMPLE_BODY \
@@ -394,15 +467,11 @@ _Pragma("unroll") \
                     if (j == 0) store2(res_base + sidx * 2, Wf * att_v * s_w, Hf * att_v * s_h); \
                     else store1(res_base + sidx, s_a); \
                 } \
+            } else if (DEFER) { \
+                finish(d_a, d_h, d_w, d_att, d_idx); \
+                d_a = s_a; d_h = s_h; d_w = s_w; d_att = att_v; d_idx = active ? sidx : -1; \
             } else { \
- \
-                float x = (j & 1) ? s_h : s_a; \
-                x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1); \
-                s_w += __shfl_xor_sync(0xffffffffu, s_w, 1); \
-                float keep = (j & 2) ? s_w : x; \
-                keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2); \
-                if (SPLIT == 8) keep += __shfl_xor_sync(0xffffffffu, keep, 4); \
-                if (active && j < 3) store1(res_base + sidx * res_stride, keep * res_scale * (j == 0 ? 1.f : att_v)); \
+                finish(s_a, s_h, s_w, att_v, active ? sidx : -1); \
             }
         // nvcc 12.9 crashes on a generic lambda here, hence two plain lambdas sharing one body
         auto sample_steady = [&](const float4 &en, const float4 (&gr)[CH]) {
@@ -424,33 +493,44 @@ _Pragma("unroll") \
 #pragma unroll
         for (int k = 0; k < CH; ++k) g0[k] = g1[k] = g2[k] = z4;
         if (cnt > 0) {
-            issue_g(e_lo, g0);
-            issue_g(e_lo + 1, g1);
+            issue_g(e_lo, 0, g0);
+            issue_g(e_lo + 1, 1, g1);
         }
         int it = 0;
         for (; it + 3 <= full; it += 3) {
             const int e = e_lo + it;
-            issue_g(e + 2, g2);
+            issue_g(e + 2, 2, g2);
+            fetch_g(0, false, g0);
             sample_steady(lds4(ent_s + e * 16), g0);
-            issue_g(e + 3, g0);
+            issue_g(e + 3, 0, g0);
+            fetch_g(1, false, g1);
             sample_steady(lds4(ent_s + (e + 1) * 16), g1);
-            issue_g(e + 4, g1);
+            issue_g(e + 4, 1, g1);
+            fetch_g(2, false, g2);
             sample_steady(lds4(ent_s + (e + 2) * 16), g2);
         }
         const int rem = full - it + (has_tail ? 1 : 0);  // 0..3 remaining steps, the same for every group
         if (rem >= 1) {
             const int e = e_lo + it;
-            if (cnt > 0 && rem >= 3) issue_g(e + 2, g2);
+            if (cnt > 0 && rem >= 3) issue_g(e + 2, 2, g2);
+            fetch_g(0, true, g0);  // (the remainder drains the copy queue: its group count depends on rem)
             sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g0, e < e_hi);
         }
         if (rem >= 2) {
             const int e = e_lo + it + 1;
+            fetch_g(1, true, g1);
             sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g1, e < e_hi);
         }
         if (rem >= 3) {
             const int e = e_lo + it + 2;
+            fetch_g(2, true, g2);
             sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g2, e < e_hi);
         }
+        if (DEFER && SPLIT >= 4) {
+            finish(d_a, d_h, d_w, d_att, d_idx);
+            d_idx = -1;
+        }
+        if (GRING) asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing may land in a slot during the next unit
         if (cur >= 0) flush();
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -462,7 +542,18 @@ int sorted_split()
     return v;
 }
 
-bool make_params(const Problem &p, SortParams &sp, size_t &smem)
+int sorted_mode()  // bit 0: cp.async grad_out ring, bit 1: deferred reduction
+{
+    static const int v = [] { const char *e = getenv("MSDA_SORTED_MODE"); return e ? atoi(e) & 3 : 0; }();
+    return v;
+}
+bool sorted_prefetch()
+{
+    static const bool v = [] { const char *e = getenv("MSDA_SORTED_PF"); return e && atoi(e) == 1; }();
+    return v;
+}
+
+bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
 {
     if (!((p.dtype == 0 || p.dtype == 1) && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
     if (p.Lq < 1 || p.Lq > 65535 || p.P > 16 || (long long)p.Lq * p.P > kMaxSamples) return false;
@@ -486,15 +577,31 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem)
     }
     sp.units = (long long)p.N * p.M * p.L;
     smem = (size_t)sp.vrows_max * 8 * 16 + (size_t)p.Lq * p.P * 16 + (kMaxCells + 8 + 32) * sizeof(int);
-    return smem <= (size_t)p.smem_optin;
+    if (smem > (size_t)p.smem_optin) return false;
+    // three private 16-byte slots per chunk per thread for the cp.async grad_out pipeline, when they fit
+    const int split = sorted_split();
+    const size_t gring = (size_t)3 * (8 / split) * threads_for_split(split) * 16;
+    mode = sorted_mode();
+    if (smem + gring > (size_t)p.smem_optin) mode &= ~1;
+    if (mode & 1) smem += gring;
+    sp.prefetch = sorted_prefetch() ? 1 : 0;
+    return true;
 }
 
 template <typename TV, typename TM>
-cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc, SortParams &sp, size_t smem, cudaStream_t st)
+cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc, SortParams &sp, size_t smem, int mode, cudaStream_t st)
 {
     const int split = sorted_split();
-    auto kern = p.P == 4 ? (split == 2 ? bwd_sorted32_kernel<TV, TM, 4, 2> : split == 4 ? bwd_sorted32_kernel<TV, TM, 4, 4> : bwd_sorted32_kernel<TV, TM, 4, 8>)
-                         : (split == 2 ? bwd_sorted32_kernel<TV, TM, 0, 2> : split == 4 ? bwd_sorted32_kernel<TV, TM, 0, 4> : bwd_sorted32_kernel<TV, TM, 0, 8>);
+    auto pick = [&](auto pt, auto md) {
+        constexpr int PT = decltype(pt)::value, MD = decltype(md)::value;
+        return split == 2 ? bwd_sorted32_kernel<TV, TM, PT, 2, MD> : split == 4 ? bwd_sorted32_kernel<TV, TM, PT, 4, MD> : bwd_sorted32_kernel<TV, TM, PT, 8, MD>;
+    };
+    auto pick_mode = [&](auto pt) {
+        using std::integral_constant;
+        return mode == 3 ? pick(pt, integral_constant<int, 3>()) : mode == 2 ? pick(pt, integral_constant<int, 2>())
+             : mode == 1 ? pick(pt, integral_constant<int, 1>()) : pick(pt, integral_constant<int, 0>());
+    };
+    auto kern = p.P == 4 ? pick_mode(std::integral_constant<int, 4>()) : pick_mode(std::integral_constant<int, 0>());
     const int kThreads = threads_for_split(split);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -516,14 +623,16 @@ bool sorted32_supported(const Problem &p)
 {
     SortParams sp;
     size_t smem;
-    return make_params(p, sp, smem);
+    int mode;
+    return make_params(p, sp, smem, mode);
 }
 
 cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st)
 {
     SortParams sp;
     size_t smem;
-    if (!make_params(p, sp, smem)) return cudaErrorInvalidValue;
+    int mode;
+    if (!make_params(p, sp, smem, mode)) return cudaErrorInvalidValue;
     const long long n_val = (long long)p.N * p.S * p.M * p.D;
     float *acc = p.dtype == 0 ? (float *)io.grad_value : (float *)io.workspace;  // bf16: fp32 accumulation in the workspace
     if (n_val > 0) {
@@ -531,9 +640,9 @@ cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st
         if (e != cudaSuccess) return e;
     }
     if (sp.units == 0 || p.Lq == 0) return cudaSuccess;
-    cudaError_t e = p.dtype == 0      ? launch_sorted<float, float>(p, io, acc, sp, smem, st)
-                    : p.loc_dtype == 0 ? launch_sorted<bf16, float>(p, io, acc, sp, smem, st)
-                                       : launch_sorted<bf16, bf16>(p, io, acc, sp, smem, st);
+    cudaError_t e = p.dtype == 0      ? launch_sorted<float, float>(p, io, acc, sp, smem, mode, st)
+                    : p.loc_dtype == 0 ? launch_sorted<bf16, float>(p, io, acc, sp, smem, mode, st)
+                                       : launch_sorted<bf16, bf16>(p, io, acc, sp, smem, mode, st);
     if (e != cudaSuccess) return e;
     if (p.dtype == 1) return convert_f32_to_bf16(acc, io.grad_value, n_val, p.sm_count, st);
     return cudaSuccess;

@@ -88,7 +88,7 @@ int msda_backward(int dtype, int loc_dtype,
                   int device, void *stream);
 
 /* Scratch bytes msda_backward needs for this problem: the fp32 accumulator of grad_value for bf16 values, the sorted
- * sample lists of the pipelined D=32 float32 backward (about 25 MB for the S4 shape, independent of N), else 0. */
+ * sample lists of the experimental "pipe32" backward when that variant is forced (about 25 MB for the S4 shape), else 0. */
 size_t msda_backward_workspace_bytes(int dtype, int loc_dtype, int N, int S, int M, int D, int L, int Lq, int P);
 
 /*

@@ -34,7 +34,8 @@ for frames in frames_list:
             torch.cuda.synchronize()
             errs = [rel(x, y) for x, y in zip(got, ref)]
             # grad_loc / grad_attn of one sample do not depend on summation order: they must agree to rounding of the 8-lane sums
-            good = errs[0] < 2e-6 and errs[1] < 2e-6 and errs[2] < 2e-6
+            tol = float(os.environ.get("CHECK_TOL", "2e-6"))
+            good = errs[0] < tol and errs[1] < tol and errs[2] < tol
             ok &= good
             print("N=%d edge=%d rep=%d %s vs %s: gv %.2e gl %.2e ga %.2e %s" % (frames, edge, rep, pkg.last_variant("backward"), base, *errs, "ok" if good else "MISMATCH"), flush=True)
 sets = [synth_inputs(torch, 40, 3 + i, torch.float32, torch.float32, dev) for i in range(4)]
