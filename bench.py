@@ -306,7 +306,7 @@ def run_ours(args):
     e2e_s = max_over_ranks(e2e_s, dev)
     windows.append((t0, t1))
     e2e = {"value": world * nF / e2e_s, "unit": UNIT, "h2d_bytes_per_step": xfer["h2d"], "d2h_bytes_per_step": xfer["d2h"],
-           "ms_per_step": e2e_s * 1e3, "api": "combo_avs_b200.host_api.HostPipeline.forward_backward (pinned host tensors, %d-frame chunks, 3 streams)" % args.e2e_chunk}
+           "ms_per_step": e2e_s * 1e3, "api": "combo_avs_b200.host_api.HostPipeline.forward_backward -> msda_forward_backward_host (C ABI; pinned host tensors, %d-frame chunks, 3 streams, 3 staging slots)" % args.e2e_chunk}
 
     clocks = sampler.stop(windows) if sampler else None
 
@@ -344,7 +344,7 @@ def main():
     ap.add_argument("--frames", type=int, default=40, help="frames per GPU per step (S4: 8 clips x 5 frames)")
     ap.add_argument("--fwd-variant", default=None)
     ap.add_argument("--bwd-variant", default=None)
-    ap.add_argument("--e2e-chunk", type=int, default=8)
+    ap.add_argument("--e2e-chunk", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

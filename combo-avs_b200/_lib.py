@@ -21,6 +21,10 @@ EXPORTS = (
     "msda_launch_count",
     "msda_last_error",
     "msda_version",
+    "msda_host_pipeline_create",
+    "msda_host_pipeline_destroy",
+    "msda_host_pipeline_error",
+    "msda_forward_backward_host",
 )
 
 _lib = None
@@ -62,6 +66,15 @@ def load():
     lib.msda_last_error.restype = ctypes.c_char_p
     lib.msda_version.argtypes = []
     lib.msda_version.restype = i
+    lib.msda_host_pipeline_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), i, i, i]
+    lib.msda_host_pipeline_create.restype = i
+    lib.msda_host_pipeline_destroy.argtypes = [vp]
+    lib.msda_host_pipeline_destroy.restype = i
+    lib.msda_host_pipeline_error.argtypes = [vp]
+    lib.msda_host_pipeline_error.restype = ctypes.c_char_p
+    lib.msda_forward_backward_host.argtypes = [vp, i, i, vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i,
+                                               ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    lib.msda_forward_backward_host.restype = i
     _lib = lib
     return lib
 

@@ -106,6 +106,26 @@ uint64_t msda_launch_count(void);
 const char *msda_last_error(void); /* thread-local, never NULL */
 int msda_version(void);
 
+/*
+ * Host-buffer entry point: forward + backward of the core on tensors in HOST memory (pinned memory makes the copies
+ * asynchronous).  The batch is cut into chunks of `chunk_frames` frames that flow through three streams owned by the
+ * pipeline object (host->device copies, kernels, device->host copies) with `slots` (2..4) device staging buffers in
+ * rotation, so PCIe runs full duplex and the kernels hide under the copies.  Semantics per frame are exactly
+ * msda_forward followed by msda_backward (same reference lines); the host geometry arrays are required.  The call
+ * returns when all four results are in host memory.  h2d_bytes / d2h_bytes (optional) receive the bytes moved.
+ * A pipeline object serves one call at a time (not re-entrant); create one per thread / device.
+ */
+typedef struct msda_host_pipeline msda_host_pipeline;
+int msda_host_pipeline_create(msda_host_pipeline **out, int device, int chunk_frames, int slots);
+int msda_host_pipeline_destroy(msda_host_pipeline *p);
+const char *msda_host_pipeline_error(const msda_host_pipeline *p);
+int msda_forward_backward_host(msda_host_pipeline *p, int dtype, int loc_dtype,
+                               const void *value, const int64_t *shapes_host, const int64_t *level_start_host,
+                               const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                               void *output, void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
+                               int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
+                               uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+
 #ifdef __cplusplus
 }
 #endif

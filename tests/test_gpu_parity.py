@@ -335,3 +335,48 @@ def test_non_default_stream_and_autograd_thread(pkg):
     with torch.cuda.stream(s):
         out, gv, gl, ga = run_op(pkg, d)
     assert rel_err(out, ref[0]) < 1e-5 and rel_err(gv, ref[1]) < 1e-4
+
+
+# ----------------------------------------------------------------------------- host-buffer entry point (native pipeline)
+@pytest.mark.parametrize("N,chunk,slots", [(7, 3, 2), (5, 4, 3), (12, 2, 4), (2, 8, 3)])
+def test_host_pipeline_matches_oracle_and_device_path(pkg, N, chunk, slots):
+    """msda_forward_backward_host (C ABI): ragged chunking, slot rotation and copies must not change any result."""
+    from combo_avs_b200.host_api import HostPipeline
+    d = make_inputs(N, S4_SHAPES, M=8, D=32, Lq=1029, P=4, seed=100 + N, lo=-0.2, hi=1.2)
+    f32 = lambda k: torch.from_numpy(np.ascontiguousarray(d[k])).float()
+    hv, hl, ha, hg = (f32(k).pin_memory() for k in ("value", "loc", "attn", "grad_out"))
+    shapes, start = _dev(d["shapes"]), _dev(d["start"])
+    out, gv, gl, ga = (torch.empty_like(t).pin_memory() for t in (hg, hv, hl, ha))
+    pipe = HostPipeline("cuda:0", chunk_frames=chunk, slots=slots)
+    for rep in range(3):  # slots are reused across calls
+        out.zero_(); gv.zero_(); gl.zero_(); ga.zero_()
+        up, down = pipe.forward_backward(hv, shapes, start, hl, ha, hg, out, gv, gl, ga, 128)
+        assert up == sum(t.numel() * 4 for t in (hv, hl, ha, hg)) and down == up
+        # the same kernels on the whole batch in device memory
+        o2 = pkg.ms_deform_attn_forward(hv.cuda(), shapes, start, hl.cuda(), ha.cuda(), 128)
+        gv2, gl2, ga2 = pkg.ms_deform_attn_backward(hv.cuda(), shapes, start, hl.cuda(), ha.cuda(), hg.cuda(), 128)
+        assert torch.equal(out, o2.cpu()) and torch.equal(gl, gl2.cpu()) and torch.equal(ga, ga2.cpu())
+        assert rel_err(gv.numpy(), gv2.cpu().numpy()) < 1e-5  # grad_value sums in a different order per launch
+    d32 = dict(d, value=hv.numpy(), loc=hl.numpy(), attn=ha.numpy(), grad_out=hg.numpy())
+    ref = oracle_all(d32)
+    assert rel_err(out.numpy(), ref[0]) < FWD_TOL[torch.float32]
+    assert rel_err(gv.numpy(), ref[1]) < BWD_TOL[torch.float32]
+    check_grad_loc(gl.numpy(), ref[2], d32, BWD_TOL[torch.float32])
+    assert rel_err(ga.numpy(), ref[3]) < BWD_TOL[torch.float32]
+    pipe.close()
+
+
+def test_host_pipeline_rejects_device_tensors(pkg):
+    from combo_avs_b200.host_api import HostPipeline
+    d = make_inputs(1, S4_SHAPES, M=8, D=32, Lq=300, P=4, seed=1)
+    t = {k: torch.from_numpy(np.ascontiguousarray(d[k])).float() for k in ("value", "loc", "attn", "grad_out")}
+    shapes, start = _dev(d["shapes"]), _dev(d["start"])
+    pipe = HostPipeline("cuda:0")
+    res = [torch.empty_like(t[k]) for k in ("grad_out", "value", "loc", "attn")]
+    with pytest.raises(RuntimeError):
+        pipe.forward_backward(t["value"].cuda(), shapes, start, t["loc"], t["attn"], t["grad_out"], *res)
+    with pytest.raises(RuntimeError):
+        pipe.forward_backward(t["value"], shapes, start, t["loc"], t["attn"][:, ::2], t["grad_out"], *res)
+    pipe.forward_backward(t["value"], shapes, start, t["loc"], t["attn"], t["grad_out"], *res)  # pageable memory still works
+    assert torch.isfinite(res[0]).all()
+    pipe.close()
