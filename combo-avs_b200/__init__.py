@@ -10,12 +10,13 @@ from . import _lib
 
 _lib.load()  # hard requirement: no extension, no package
 
-from .functions import MSDeformAttnFunction, ms_deform_attn_backward, ms_deform_attn_forward  # noqa: E402
+from .functions import MSDeformAttnFunction, MSDeformAttnPrologueFunction, ms_deform_attn_backward, ms_deform_attn_forward  # noqa: E402
 from .modules import MSDeformAttn  # noqa: E402
 from ._lib import last_variant, launch_count, select_variant, variant_names  # noqa: E402
 
 __all__ = [
     "MSDeformAttnFunction",
+    "MSDeformAttnPrologueFunction",
     "MSDeformAttn",
     "ms_deform_attn_forward",
     "ms_deform_attn_backward",

@@ -25,6 +25,9 @@ EXPORTS = (
     "msda_host_pipeline_destroy",
     "msda_host_pipeline_error",
     "msda_forward_backward_host",
+    "msda_fused_supported",
+    "msda_fused_forward",
+    "msda_fused_backward",
 )
 
 _lib = None
@@ -75,6 +78,12 @@ def load():
     lib.msda_forward_backward_host.argtypes = [vp, i, i, vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i,
                                                ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     lib.msda_forward_backward_host.restype = i
+    lib.msda_fused_supported.argtypes = [i, i, i, i, i, i, i, i, ip, ip, i]
+    lib.msda_fused_supported.restype = i
+    lib.msda_fused_forward.argtypes = [i, vp, ip, ip, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, ip, ip, i, vp]
+    lib.msda_fused_forward.restype = i
+    lib.msda_fused_backward.argtypes = [i, vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, ip, ip, i, vp]
+    lib.msda_fused_backward.restype = i
     _lib = lib
     return lib
 

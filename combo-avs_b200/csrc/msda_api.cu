@@ -277,4 +277,83 @@ int msda_backward(int dtype, int loc_dtype, const void *value, const int64_t *sp
     return MSDA_OK;
 }
 
+
+/* ---- fused module prologue (ops/modules/ms_deform_attn.py:102-116) ------------------------------------------ */
+
+int msda_fused_supported(int dtype, int N, int S, int M, int D, int L, int Lq, int P, const int64_t *shapes_host,
+                         const int64_t *level_start_host, int device)
+{
+    if (dtype != MSDA_F32 || !shapes_host || !level_start_host || N <= 0 || Lq <= 0 || S <= 0) return 0;
+    Problem p;
+    int dummy = 0;
+    // pointers are only inspected for NULL-ness by the support queries
+    int rc = fill_problem(p, dtype, dtype, &dummy, (const int64_t *)&dummy, (const int64_t *)&dummy, &dummy, &dummy, N, S, M, D, L, Lq, P, 128,
+                          shapes_host, level_start_host, device);
+    if (rc != MSDA_OK) return 0;
+    p.ref = &dummy;
+    p.attn_out = &dummy;
+    return slab32_supported(p) && sorted32_supported(p) ? 1 : 0;
+}
+
+int msda_fused_forward(int dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *reference_points, const void *sampling_offsets, const void *attention_logits, void *output,
+                       void *attention_weights_out, int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
+                       const int64_t *shapes_host, const int64_t *level_start_host, int device, void *stream)
+{
+    Problem p;
+    int rc = fill_problem(p, dtype, dtype, value, spatial_shapes, level_start_index, sampling_offsets, attention_logits, N, S, M, D, L, Lq,
+                          P, im2col_step, shapes_host, level_start_host, device);
+    if (rc != MSDA_OK) return rc;
+    if (N == 0 || Lq == 0) return MSDA_OK;
+    if (!output || !reference_points || !attention_weights_out) return fail(MSDA_ERR_NULL, "NULL pointer in fused forward");
+    p.ref = reference_points;
+    p.attn_out = attention_weights_out;
+    if (dtype != MSDA_F32 || !slab32_supported(p))
+        return fail(MSDA_ERR_VARIANT, "fused forward needs f32, D=32, L*P %% 4 == 0, host geometry and a padded slab that fits shared memory");
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    e = fwd_slab32(p, output, (cudaStream_t)stream);
+    g_last_variant[0].store("slab32+prologue");
+    if (e != cudaSuccess) return cuda_fail(e, "msda_fused_forward launch");
+    return MSDA_OK;
+}
+
+int msda_fused_backward(int dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *reference_points, const void *sampling_offsets, const void *attention_weights,
+                        const void *grad_output, void *grad_value, void *grad_sampling_offsets, void *grad_attention_logits, int N,
+                        int S, int M, int D, int L, int Lq, int P, int im2col_step, const int64_t *shapes_host,
+                        const int64_t *level_start_host, int device, void *stream)
+{
+    Problem p;
+    int rc = fill_problem(p, dtype, dtype, value, spatial_shapes, level_start_index, sampling_offsets, attention_weights, N, S, M, D, L, Lq,
+                          P, im2col_step, shapes_host, level_start_host, device);
+    if (rc != MSDA_OK) return rc;
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_val = (size_t)N * S * M * D;
+    if (N == 0 || Lq == 0) {
+        if (n_val > 0 && grad_value) {
+            e = cudaMemsetAsync(grad_value, 0, n_val * elem_size(dtype), st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_value)");
+        }
+        return MSDA_OK;
+    }
+    if (!grad_output || !grad_sampling_offsets || !grad_attention_logits || !reference_points || (n_val > 0 && !grad_value))
+        return fail(MSDA_ERR_NULL, "NULL pointer in fused backward");
+    p.ref = reference_points;
+    if (dtype != MSDA_F32 || !sorted32_supported(p))
+        return fail(MSDA_ERR_VARIANT, "fused backward needs f32, D=32, host geometry, Lq*P <= 4608, (H+1)*(W+1) <= 1024 per level");
+    // the sorted backward leaves d(out)/d(softmaxed weight) in grad_attention_logits; the softmax backward then runs in place
+    BackwardIO io{grad_output, grad_value, grad_sampling_offsets, grad_attention_logits, nullptr, 0};
+    e = bwd_sorted32(p, io, st);
+    if (e == cudaSuccess)
+        e = softmax_backward_rows((const float *)attention_weights, (float *)grad_attention_logits, (long long)N * Lq * M, L * P, p.sm_count, st);
+    g_last_variant[1].store("sorted32+prologue");
+    if (e != cudaSuccess) return cuda_fail(e, "msda_fused_backward launch");
+    return MSDA_OK;
+}
+
 }  // extern "C"

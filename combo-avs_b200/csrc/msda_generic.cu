@@ -204,4 +204,44 @@ cudaError_t bwd_generic(const Problem &p, const BackwardIO &io, cudaStream_t st)
     return cudaGetLastError();
 }
 
+
+namespace {
+// one thread per (frame, query, head) row: grad_logit_j = a_j * (g_j - sum_k a_k g_k)   (softmax backward, in place on g)
+__global__ void softmax_backward_kernel(const float *__restrict__ attn, float *__restrict__ grad, long long rows, int LP)
+{
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+        const float *a = attn + r * LP;
+        float *g = grad + r * LP;
+        float dot = 0.f;
+        if ((LP & 3) == 0) {
+            for (int i = 0; i < LP; i += 4) {
+                const float4 av = *reinterpret_cast<const float4 *>(a + i), gv = *reinterpret_cast<const float4 *>(g + i);
+                dot += av.x * gv.x + av.y * gv.y + av.z * gv.z + av.w * gv.w;
+            }
+            for (int i = 0; i < LP; i += 4) {
+                const float4 av = *reinterpret_cast<const float4 *>(a + i);
+                float4 gv = *reinterpret_cast<const float4 *>(g + i);
+                gv.x = av.x * (gv.x - dot); gv.y = av.y * (gv.y - dot); gv.z = av.z * (gv.z - dot); gv.w = av.w * (gv.w - dot);
+                *reinterpret_cast<float4 *>(g + i) = gv;
+            }
+        } else {
+            for (int i = 0; i < LP; ++i) dot += a[i] * g[i];
+            for (int i = 0; i < LP; ++i) g[i] = a[i] * (g[i] - dot);
+        }
+    }
+}
+}  // namespace
+
+cudaError_t softmax_backward_rows(const float *attn, float *grad, long long rows, int LP, int sm_count, cudaStream_t st)
+{
+    if (rows <= 0) return cudaSuccess;
+    const int threads = 256;
+    long long blocks = (rows + threads - 1) / threads;
+    const long long cap = (long long)sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    softmax_backward_kernel<<<(int)blocks, threads, 0, st>>>(attn, grad, rows, LP);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace msda

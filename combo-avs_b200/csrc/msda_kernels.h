@@ -21,6 +21,11 @@ struct Problem {
     LevelTable table;  // valid iff have_host
     int sm_count;
     int smem_optin;    // max dynamic shared memory per block (opt-in)
+    // fused module prologue (ops/modules/ms_deform_attn.py:102-116): when `ref` is set, `loc` holds the raw sampling OFFSETS and
+    // locations are ref + offset / (W_l, H_l); in the forward `attn` then holds the raw attention LOGITS (softmax over L*P is
+    // taken in the kernel and written to `attn_out`), in the backward it holds the softmaxed weights saved by the forward.
+    const void *ref = nullptr;   // [N, Lq, L, 2] (x, y), dtype of loc
+    void *attn_out = nullptr;    // [N, Lq, M, L, P]
 };
 
 struct BackwardIO {
@@ -57,5 +62,8 @@ cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st
 bool pipe32_supported(const Problem &p);
 size_t bwd_pipe32_workspace(int dtype, int D, int Lq, int P);
 cudaError_t bwd_pipe32(const Problem &p, const BackwardIO &io, cudaStream_t st);
+
+// softmax backward over the last L*P entries of every (frame, query, head) row, in place on grad (msda_generic.cu)
+cudaError_t softmax_backward_rows(const float *attn, float *grad, long long rows, int LP, int sm_count, cudaStream_t st);
 
 }  // namespace msda

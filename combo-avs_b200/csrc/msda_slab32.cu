@@ -34,6 +34,7 @@ struct SlabParams {
     unsigned wrecip[kMaxLevels];  // ceil(2^32 / W): pixel / W == umulhi(pixel, wrecip) for pixel < 2^16
     unsigned precip;          // ceil(2^32 / (3*L*P/4)) for the metadata staging index split
     int padded_rows;          // total rows of the padded slab
+    int fused;                // loc = raw offsets, attn = raw logits: transform the staged rows in place (needs STAGE)
     int qpp;                  // queries per pass
     int pps;                  // passes per slab
     long long units;          // N*M*pps
@@ -156,7 +157,8 @@ __device__ __forceinline__ void floor_split(float x, float &fl, int &i)
 // pieces issued by consecutive lanes touch each 128-byte line once, instead of once per sample per query.
 template <typename TM>
 __device__ __forceinline__ void stage_meta(TM *meta, const TM *__restrict__ loc, const TM *__restrict__ attn,
-                                           const SlabParams &sp, int LP, long long nm, int q0, int cnt)
+                                           const SlabParams &sp, int LP, long long nm, int q0, int cnt,
+                                           TM *refs = nullptr, const TM *__restrict__ ref = nullptr)
 {
     const long long n = nm / sp.M;
     const int m = (int)(nm - n * sp.M);
@@ -170,6 +172,13 @@ __device__ __forceinline__ void stage_meta(TM *meta, const TM *__restrict__ loc,
         const TM *src = pc < loc_pieces ? lbase + ql * lstride + pc * 4 : abase + ql * astride + (pc - loc_pieces) * 4;
         if (sizeof(TM) == 4) cp_async16(meta + ql * (3 * LP) + pc * 4, src);
         else cp_async8(meta + ql * (3 * LP) + pc * 4, src);
+    }
+    if (refs != nullptr) {  // fused prologue: the pass's reference points, [cnt][L][2] contiguous in global memory
+        const TM *rsrc = ref + ((n * sp.Lq + q0) * sp.L) * 2;
+        for (int i = threadIdx.x; i < cnt * sp.L; i += blockDim.x) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(refs + i * 2);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(rsrc + i * 2) : "memory");
+        }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -190,7 +199,7 @@ __device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
 template <typename TV, typename TM, int P_T, bool STAGE, int SPLIT>
 __global__ void __launch_bounds__(SPLIT == 4 ? 768 : 512, 1)
 fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, const TM *__restrict__ attn,
-                  TV *__restrict__ out, const __grid_constant__ SlabParams sp)
+                  TV *__restrict__ out, const TM *__restrict__ ref, TM *__restrict__ attn_out, const __grid_constant__ SlabParams sp)
 {
     constexpr int CH = 8 / SPLIT;  // 16-byte chunks (4 channels) per lane
     extern __shared__ float4 slab[];
@@ -198,6 +207,10 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
     const int LP = sp.L * P;
     TM *meta0 = reinterpret_cast<TM *>(slab + (size_t)sp.padded_rows * 8);  // two staging buffers of qpp rows
     const int meta_stride = sp.qpp * 3 * LP;
+    // fused prologue: two buffers of qpp x L reference points after the metadata buffers
+    TM *refs0 = meta0 + 2 * meta_stride;
+    const int ref_stride = sp.qpp * sp.L * 2;
+    const bool fused = STAGE && sizeof(TM) == 4 && sp.fused != 0;
     for (int l = 0; l < sp.L; ++l) {  // zero the one-pixel border of every level once; slab loads only ever write interiors
         const int H = sp.H[l], Wp = sp.W[l] + 2;
         float4 *lv = slab + (size_t)sp.prow0[l] * 8;
@@ -235,7 +248,7 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
     if (STAGE && u_lo < u_hi) {
         long long nm; int q0, cnt;
         pass_range(u_lo, nm, q0, cnt);
-        stage_meta(meta0, loc, attn, sp, LP, nm, q0, cnt);
+        stage_meta(meta0, loc, attn, sp, LP, nm, q0, cnt, fused ? refs0 : nullptr, ref);
     }
     for (long long u = u_lo; u < u_hi; ++u) {
         long long nm; int q0, cnt;
@@ -252,7 +265,8 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
             if (u + 1 < u_hi) {
                 long long nm2; int q02, cnt2;
                 pass_range(u + 1, nm2, q02, cnt2);
-                stage_meta(meta0 + ((u + 1 - u_lo) & 1) * meta_stride, loc, attn, sp, LP, nm2, q02, cnt2);
+                stage_meta(meta0 + ((u + 1 - u_lo) & 1) * meta_stride, loc, attn, sp, LP, nm2, q02, cnt2,
+                           fused ? refs0 + ((u + 1 - u_lo) & 1) * ref_stride : nullptr, ref);
             } else {
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
@@ -265,6 +279,38 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
         using TM2 = typename Pair<TM>::type;
         const TM2 *loc2 = STAGE ? reinterpret_cast<const TM2 *>(meta + ql * 3 * LP) : reinterpret_cast<const TM2 *>(loc) + qm * LP;
         const TM *att = STAGE ? meta + ql * 3 * LP + 2 * LP : attn + qm * LP;
+        if (fused) {
+            // Module prologue in place on the staged row of (query, head) (ops/modules/ms_deform_attn.py:102-116): lane 0 of the
+            // pair turns the L*P logits into softmax weights (and stores them for the backward), lane 1 turns the offsets into
+            // locations ref + offset / (W_l, H_l) -- fp32 division and addition, as the reference's elementwise kernels do.
+            float *row = reinterpret_cast<float *>(const_cast<TM *>(meta)) + ql * 3 * LP;
+            if (live && part == 0) {
+                float *lg = row + 2 * LP;
+                float mx = lg[0];
+                for (int i = 1; i < LP; ++i) mx = fmaxf(mx, lg[i]);
+                float sum = 0.f;
+                for (int i = 0; i < LP; ++i) {
+                    const float e = expf(lg[i] - mx);
+                    lg[i] = e;
+                    sum += e;
+                }
+                for (int i = 0; i < LP; ++i) lg[i] = __fdiv_rn(lg[i], sum);
+                float4 *ao = reinterpret_cast<float4 *>(reinterpret_cast<float *>(attn_out) + qm * LP);  // LP % 4 == 0 (STAGE)
+                for (int i = 0; i < LP / 4; ++i) ao[i] = reinterpret_cast<const float4 *>(lg)[i];
+            }
+            if (live && part == SPLIT - 1) {
+                const float *rf = reinterpret_cast<const float *>(refs0 + ((u - u_lo) & 1) * ref_stride) + ql * sp.L * 2;
+                for (int l = 0; l < sp.L; ++l) {
+                    const float Wf = (float)sp.W[l], Hf = (float)sp.H[l], rx = rf[2 * l], ry = rf[2 * l + 1];
+                    for (int p = 0; p < P; ++p) {
+                        float *xy = row + 2 * (l * P + p);
+                        xy[0] = __fadd_rn(rx, __fdiv_rn(xy[0], Wf));
+                        xy[1] = __fadd_rn(ry, __fdiv_rn(xy[1], Hf));
+                    }
+                }
+            }
+            __syncthreads();  // both lanes of a pair read the whole row below
+        }
         f4p acc[CH];
 #pragma unroll
         for (int k = 0; k < CH; ++k) acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
@@ -380,6 +426,13 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
     const size_t meta_bytes = 2 * (size_t)sp.qpp * 3 * LP * (p.loc_dtype == 1 ? 2 : 4);
     stage = (LP % 4 == 0) && smem_bytes + meta_bytes <= (size_t)p.smem_optin;
     if (stage) smem_bytes += meta_bytes;
+    sp.fused = 0;
+    if (p.ref != nullptr) {  // fused prologue: needs the staged path, float32 metadata and room for the reference points
+        const size_t ref_bytes = 2 * (size_t)sp.qpp * p.L * 2 * 4;
+        if (!stage || p.loc_dtype != 0 || split != 2 || smem_bytes + ref_bytes > (size_t)p.smem_optin || p.attn_out == nullptr) return false;
+        smem_bytes += ref_bytes;
+        sp.fused = 1;
+    }
     return true;
 }
 
@@ -393,7 +446,7 @@ cudaError_t launch_typed(const Problem &p, void *out, cudaStream_t st, const Sla
                                   : (s4 ? fwd_slab32_kernel<TV, TM, 0, false, 4> : fwd_slab32_kernel<TV, TM, 0, false, 2>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, threads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (TV *)out, sp);
+    kern<<<grid, threads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (TV *)out, (const TM *)p.ref, (TM *)p.attn_out, sp);
     count_launch();
     return cudaGetLastError();
 }

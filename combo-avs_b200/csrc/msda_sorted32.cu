@@ -46,6 +46,7 @@ struct SortParams {
     int rem;                 // leftover units (units - base*grid), each cut into `parts` pieces: one piece per CTA
     int parts;
     int prefetch;            // L2-prefetch the next unit's inputs during the walk
+    int fused;               // `loc` holds raw offsets: location = ref + offset / (W, H); grad_loc is then d/d(offset)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
@@ -112,7 +113,7 @@ template <typename TV, typename TM, int P_T, int SPLIT, int MODE>
 __global__ void __launch_bounds__(threads_for_split(SPLIT), 1)
 bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, const TM *__restrict__ attn,
                     const TV *__restrict__ grad_out, float *__restrict__ grad_value, TM *__restrict__ grad_loc,
-                    TM *__restrict__ grad_attn, const __grid_constant__ SortParams sp)
+                    TM *__restrict__ grad_attn, const TM *__restrict__ ref, const __grid_constant__ SortParams sp)
 {
     constexpr int kThreads = threads_for_split(SPLIT), CH = 8 / SPLIT;
     constexpr int kGroups = kThreads / SPLIT, kRounds = (kMaxSamples + kThreads - 1) / kThreads;
@@ -176,7 +177,12 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
             sa[r] = 0.f;
             if (i < EP) {
                 const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
-                const float2 xy = load2(locb + 2 * (q * qstride + p));
+                float2 xy = load2(locb + 2 * (q * qstride + p));
+                if (sp.fused) {  // module prologue (ms_deform_attn.py:110-112): reference point + offset / (W_l, H_l)
+                    const float2 rf = load2(ref + ((n * Lq + q) * sp.L + l) * 2);
+                    xy.x = __fadd_rn(rf.x, __fdiv_rn(xy.x, Wf));
+                    xy.y = __fadd_rn(rf.y, __fdiv_rn(xy.y, Hf));
+                }
                 sx[r] = xy.x;
                 sy[r] = xy.y;
                 sa[r] = load1(att + q * qstride + p);
@@ -337,7 +343,8 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         // result stores: SPLIT >= 4: lane 0 grad_attn, lane 1 grad_loc.y, lane 2 grad_loc.x; SPLIT == 2: lane 0 grad_loc (float2), lane 1 grad_attn
         TM *res_base = SPLIT >= 4 ? (j == 0 ? gatt : gloc + (j == 1 ? 1 : 0)) : (j == 0 ? gloc : gatt);
         int res_stride = SPLIT >= 4 ? (j == 0 ? 1 : 2) : (j == 0 ? 2 : 1);
-        float res_scale = j == 0 ? 1.f : (j == 1 ? Hf : Wf);
+        // d(loc)/d(offset) = 1 / (W, H) cancels the (W, H) factor of grad_sampling_loc (cuh:126-127) in the fused form
+        float res_scale = (j == 0 || sp.fused) ? 1.f : (j == 1 ? Hf : Wf);
         pin(res_base); pin(res_stride); pin(res_scale); pin(gobase); pin(gbase);
         int cur = -1, inmask = 0;
         float *gp = gbase;             // grad_value row of the current cell's top-left neighbour
@@ -464,7 +471,7 @@ _Pragma("unroll") \
                 s_h += __shfl_xor_sync(0xffffffffu, s_h, 1); \
                 s_w += __shfl_xor_sync(0xffffffffu, s_w, 1); \
                 if (active) { \
-                    if (j == 0) store2(res_base + sidx * 2, Wf * att_v * s_w, Hf * att_v * s_h); \
+                    if (j == 0) store2(res_base + sidx * 2, (sp.fused ? 1.f : Wf) * att_v * s_w, (sp.fused ? 1.f : Hf) * att_v * s_h); \
                     else store1(res_base + sidx, s_a); \
                 } \
             } else if (DEFER) { \
@@ -585,6 +592,8 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
     if (smem + gring > (size_t)p.smem_optin) mode &= ~1;
     if (mode & 1) smem += gring;
     sp.prefetch = sorted_prefetch() ? 1 : 0;
+    sp.fused = p.ref != nullptr ? 1 : 0;
+    if (sp.fused && p.loc_dtype != 0) return false;
     return true;
 }
 
@@ -612,7 +621,7 @@ cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc,
     if (sp.parts > 4) sp.parts = 4;
     if (sp.parts < 1) sp.parts = 1;
     kern<<<grid, kThreads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (const TV *)io.grad_out, gv_acc,
-                                       (TM *)io.grad_loc, (TM *)io.grad_attn, sp);
+                                       (TM *)io.grad_loc, (TM *)io.grad_attn, (const TM *)p.ref, sp);
     count_launch();
     return cudaGetLastError();
 }

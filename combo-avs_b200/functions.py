@@ -146,3 +146,77 @@ class MSDeformAttnFunction(Function):
             value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
             grad_output.contiguous(), ctx.im2col_step, ctx.geometry)
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+# ------------------------------------------------------------------------------------------------ fused module prologue
+def fused_prologue_supported(value, spatial_shapes, level_start_index, reference_points, sampling_offsets):
+    """True when msda_fused_forward / msda_fused_backward (include/msda_b200.h) can take this call: CUDA float32 tensors,
+    2-d reference points that need no gradient, and a shape the slab / sorted kernels hold in shared memory."""
+    if not (value.is_cuda and value.dtype == torch.float32 and sampling_offsets.dtype == torch.float32):
+        return False
+    if reference_points.shape[-1] != 2 or reference_points.requires_grad or reference_points.dtype != torch.float32:
+        return False
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_offsets.shape[1], sampling_offsets.shape[4]
+    hs, hl = _host_geometry(spatial_shapes, level_start_index)[:2]
+    dev = value.device.index if value.device.index is not None else torch.cuda.current_device()
+    return bool(_lib.load().msda_fused_supported(_lib.F32, N, S, M, D, L, Lq, P, hs, hl, dev))
+
+
+class MSDeformAttnPrologueFunction(Function):
+    """The op with the module's prologue folded in (ops/modules/ms_deform_attn.py:102-116 + functions/ms_deform_attn_func.py:32-50):
+    apply(value[N,S,M,D], spatial_shapes, level_start_index, reference_points[N,Lq,L,2], sampling_offsets[N,Lq,M,L,P,2],
+          attention_logits[N,Lq,M,L*P], im2col_step) == MSDeformAttnFunction.apply(value, shapes, start,
+          reference_points[:, :, None, :, None, :] + sampling_offsets / (W_l, H_l), softmax(attention_logits, -1), im2col_step).
+    backward returns (grad_value, None, None, None, grad_sampling_offsets, grad_attention_logits, None)."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits, im2col_step):
+        named = (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                 ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attention_logits", attention_logits))
+        _check_inputs(named, value)
+        N, S, M, D = value.shape
+        L = spatial_shapes.shape[0]
+        Lq, P = sampling_offsets.shape[1], sampling_offsets.shape[4]
+        if tuple(sampling_offsets.shape) != (N, Lq, M, L, P, 2) or attention_logits.numel() != N * Lq * M * L * P or \
+                tuple(reference_points.shape) != (N, Lq, L, 2):
+            raise RuntimeError("inconsistent shapes: value %s, reference_points %s, sampling_offsets %s, attention_logits %s" %
+                               (tuple(value.shape), tuple(reference_points.shape), tuple(sampling_offsets.shape), tuple(attention_logits.shape)))
+        if not (value.dtype == sampling_offsets.dtype == attention_logits.dtype == reference_points.dtype == torch.float32):
+            raise RuntimeError("the fused prologue takes float32 tensors")
+        ctx.im2col_step = im2col_step
+        ctx.geometry = _host_geometry(spatial_shapes, level_start_index)
+        hs, hl = ctx.geometry[:2]
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        attn = torch.empty((N, Lq, M, L, P), dtype=value.dtype, device=value.device)
+        dev = value.device.index if value.device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = _lib.load().msda_fused_forward(_lib.F32, _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(reference_points),
+                                            _ptr(sampling_offsets), _ptr(attention_logits), _ptr(out), _ptr(attn), N, S, M, D, L, Lq, P,
+                                            int(im2col_step), hs, hl, dev, ctypes.c_void_p(stream))
+        _lib.check(rc)
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn)
+        ctx.logits_shape = attention_logits.shape
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn = ctx.saved_tensors
+        N, S, M, D = value.shape
+        L = spatial_shapes.shape[0]
+        Lq, P = sampling_offsets.shape[1], sampling_offsets.shape[4]
+        grad_output = grad_output.contiguous()
+        hs, hl = ctx.geometry[:2]
+        grad_value = torch.empty_like(value)
+        grad_off = torch.empty_like(sampling_offsets)
+        grad_logits = torch.empty(ctx.logits_shape, dtype=value.dtype, device=value.device)
+        dev = value.device.index if value.device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = _lib.load().msda_fused_backward(_lib.F32, _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(reference_points),
+                                             _ptr(sampling_offsets), _ptr(attn), _ptr(grad_output), _ptr(grad_value), _ptr(grad_off),
+                                             _ptr(grad_logits), N, S, M, D, L, Lq, P, int(ctx.im2col_step), hs, hl, dev,
+                                             ctypes.c_void_p(stream))
+        _lib.check(rc)
+        return grad_value, None, None, None, grad_off, grad_logits, None

@@ -107,6 +107,35 @@ const char *msda_last_error(void); /* thread-local, never NULL */
 int msda_version(void);
 
 /*
+ * Fused module prologue.  The reference's MSDeformAttn.forward computes, between its Linear
+ * layers and the op (ops/modules/ms_deform_attn.py:102-116):
+ *     attention_weights  = softmax(attention_logits.view(N, Lq, M, L*P), -1)
+ *     sampling_locations = reference_points[:, :, None, :, None, :] + sampling_offsets / (W_l, H_l)      (2-d reference points)
+ * as separate elementwise kernels that write and re-read 31.6 MB of locations and 15.8 MB of weights per layer.  These two
+ * entry points take the Linear outputs directly: the forward stages offsets / logits / reference points of a pass in shared
+ * memory, transforms them in place (fp32 division, addition, expf: the reference's arithmetic) and writes the softmaxed weights
+ * once (attention_weights_out, needed by the backward); the backward rebuilds the locations while it sorts, writes
+ * d/d(sampling_offsets) directly (the (W, H) factors of ms_deform_im2col_cuda.cuh:126-127 cancel) and finishes with an
+ * in-place softmax backward, so grad_attention_logits is d/d(logits).  reference_points: [N, Lq, L, 2] (x, y), no gradient.
+ * float32, D = 32, host geometry required; msda_fused_supported() tells whether a shape qualifies (else compose the unfused
+ * entry points as the reference does).  Everything else (layouts, statuses, stream / device) as msda_forward / msda_backward.
+ */
+int msda_fused_supported(int dtype, int N, int S, int M, int D, int L, int Lq, int P,
+                         const int64_t *shapes_host, const int64_t *level_start_host, int device);
+int msda_fused_forward(int dtype,
+                       const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *reference_points, const void *sampling_offsets, const void *attention_logits,
+                       void *output, void *attention_weights_out,
+                       int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
+                       const int64_t *shapes_host, const int64_t *level_start_host, int device, void *stream);
+int msda_fused_backward(int dtype,
+                        const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *reference_points, const void *sampling_offsets, const void *attention_weights,
+                        const void *grad_output, void *grad_value, void *grad_sampling_offsets, void *grad_attention_logits,
+                        int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
+                        const int64_t *shapes_host, const int64_t *level_start_host, int device, void *stream);
+
+/*
  * Host-buffer entry point: forward + backward of the core on tensors in HOST memory (pinned memory makes the copies
  * asynchronous).  The batch is cut into chunks of `chunk_frames` frames that flow through three streams owned by the
  * pipeline object (host->device copies, kernels, device->host copies) with `slots` (2..4) device staging buffers in

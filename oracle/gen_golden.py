@@ -149,6 +149,33 @@ def main():
     save("module_small", query=query, src=src, ref2=ref2, ref4=ref4, mask=mask, shapes=shapes, start=start,
          y2=y2.detach(), y2_masked=y2m.detach(), y4=y4.detach(),
          **{"sd_" + k.replace(".", "__"): v for k, v in state.items()})
+    # ---- the module at the production head width (d_model 256, 8 heads -> D = 32) with gradients: pins the fused prologue ------
+    torch.manual_seed(11)
+    shapes = torch.as_tensor([(4, 4), (6, 6), (10, 10)], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    N, C = 1, 256
+    mod = MSDeformAttn(d_model=C, n_levels=3, n_heads=8, n_points=4)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.1)
+        mod.attention_weights.bias.normal_(0, 0.5)
+    query = torch.randn(N, S, C)          # float32-representable inputs and weights, evaluated by the reference in float64
+    src = torch.randn(N, S, C)
+    ref2 = torch.rand(N, S, 3, 2)
+    mask = torch.rand(N, S) < 0.1
+    wout = torch.randn(N, S, C)
+    state = {k: v.detach().clone() for k, v in mod.state_dict().items()}
+    mod = mod.double()
+    start = level_start(shapes)
+    qd, sd = query.double().requires_grad_(True), src.double().requires_grad_(True)
+    y = mod(qd, ref2.double(), sd, shapes, start, mask)
+    (y * wout.double()).sum().backward()
+    save("module_d256", query=query, src=src, ref2=ref2, mask=mask, shapes=shapes, start=start, wout=wout, y=y.detach(),
+         grad_query=qd.grad, grad_src=sd.grad,
+         grad_offsets_bias=mod.sampling_offsets.bias.grad, grad_attn_bias=mod.attention_weights.bias.grad,
+         grad_value_bias=mod.value_proj.bias.grad, grad_offsets_weight_rowsum=mod.sampling_offsets.weight.grad.sum(1),
+         grad_attn_weight_rowsum=mod.attention_weights.weight.grad.sum(1),
+         **{"sd_" + k.replace(".", "__"): v for k, v in state.items()})
     fresh = MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4)
     save("module_init_256", offsets_bias=fresh.sampling_offsets.bias.detach(),
          offsets_weight_absmax=fresh.sampling_offsets.weight.detach().abs().max(),

@@ -380,3 +380,102 @@ def test_host_pipeline_rejects_device_tensors(pkg):
     pipe.forward_backward(t["value"], shapes, start, t["loc"], t["attn"], t["grad_out"], *res)  # pageable memory still works
     assert torch.isfinite(res[0]).all()
     pipe.close()
+
+
+# ------------------------------------------------------------------------------------ fused module prologue (row f1)
+def _prologue_reference(d, off, logits, ref, grad_out):
+    """fp64: locations and weights as the reference module builds them (ms_deform_attn.py:102-112), the oracle for the op,
+    and the chain rule back to offsets / logits."""
+    shp = np.asarray(d["shapes"], dtype=np.float64)
+    norm = np.stack([shp[:, 1], shp[:, 0]], -1)[None, None, None, :, None, :]          # (W, H)
+    loc = ref[:, :, None, :, None, :] + off / norm
+    N, Lq, M, L, P, _ = off.shape
+    lg = logits.reshape(N, Lq, M, L * P)
+    e = np.exp(lg - lg.max(-1, keepdims=True))
+    attn = (e / e.sum(-1, keepdims=True)).reshape(N, Lq, M, L, P)
+    out = oracle.forward(d["value"], d["shapes"], d["start"], loc, attn)
+    gv, gl, ga = oracle.backward(d["value"], d["shapes"], d["start"], loc, attn, grad_out)
+    g_off = gl / norm
+    a, g = attn.reshape(N, Lq, M, L * P), ga.reshape(N, Lq, M, L * P)
+    g_logits = a * (g - (a * g).sum(-1, keepdims=True))
+    return dict(loc=loc, attn=attn, out=out, grad_value=gv, grad_off=g_off, grad_logits=g_logits)
+
+
+@pytest.mark.parametrize("N,spread", [(1, 1.0), (3, 6.0), (7, 40.0)])
+def test_fused_prologue_function_matches_oracle(pkg, N, spread):
+    """MSDeformAttnPrologueFunction == softmax + location arithmetic + op, against the fp64 oracle (spread = offset scale in
+    pixels: 40 throws most samples of the coarse levels off the map)."""
+    from combo_avs_b200.functions import MSDeformAttnPrologueFunction
+    rng = np.random.default_rng(50 + N)
+    d = make_inputs(N, S4_SHAPES, 8, 32, 1029, 4, seed=60 + N)
+    L, P, M, Lq = 3, 4, 8, 1029
+    off = (rng.standard_normal((N, Lq, M, L, P, 2)) * spread).astype(np.float32)
+    logits = (rng.standard_normal((N, Lq, M, L * P)) * 2).astype(np.float32)
+    ref = rng.random((N, Lq, L, 2)).astype(np.float32)
+    d64 = {k: (np.asarray(v, dtype=np.float64) if np.asarray(v).dtype.kind == "f" else v) for k, v in d.items()}
+    want = _prologue_reference(d64, off.astype(np.float64), logits.astype(np.float64), ref.astype(np.float64), d64["grad_out"])
+    v = _dev(d["value"]).requires_grad_(True)
+    o = _dev(off).requires_grad_(True)
+    lg = _dev(logits).requires_grad_(True)
+    out = MSDeformAttnPrologueFunction.apply(v, _dev(d["shapes"]), _dev(d["start"]), _dev(ref), o, lg, 128)
+    assert pkg.last_variant("forward") == "slab32+prologue"
+    out.backward(_dev(d["grad_out"]))
+    torch.cuda.synchronize()
+    assert pkg.last_variant("backward") == "sorted32+prologue"
+    assert rel_err(out.detach().cpu().numpy(), want["out"]) < FWD_TOL[torch.float32]
+    assert rel_err(v.grad.cpu().numpy(), want["grad_value"]) < BWD_TOL[torch.float32]
+    assert rel_err(lg.grad.cpu().numpy(), want["grad_logits"]) < BWD_TOL[torch.float32]
+    # d/d(offset) is discontinuous where the fp32 pixel coordinate crosses an integer, exactly like d/d(location)
+    dl = dict(d, loc=want["loc"].astype(np.float32))
+    check_grad_loc(o.grad.cpu().numpy(), want["grad_off"], dl, BWD_TOL[torch.float32])
+    # and the unfused composition of the same kernels gives the same numbers (forward bit-exact up to the exp / division ulp)
+    norm = torch.tensor([[w, h] for h, w in S4_SHAPES], dtype=torch.float32, device="cuda").view(1, 1, 1, L, 1, 2)
+    loc_t = (_dev(ref)[:, :, None, :, None, :] + _dev(off) / norm).contiguous()
+    attn_t = torch.softmax(_dev(logits), -1).view(N, Lq, M, L, P).contiguous()
+    out2 = pkg.ms_deform_attn_forward(_dev(d["value"]), _dev(d["shapes"]), _dev(d["start"]), loc_t, attn_t, 128)
+    assert rel_err(out.detach().cpu().numpy(), out2.cpu().numpy()) < 2e-6
+
+
+def test_fused_module_matches_reference_module_d256(pkg):
+    """The module at the production head width against the reference module's float64 run (tests/golden/module_d256.npz):
+    fused and unfused paths, outputs and gradients (inputs, biases, weight row sums)."""
+    g = load_golden("module_d256")
+    results = {}
+    for fused in (True, False):
+        m = pkg.MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4)
+        m.load_state_dict({k[3:].replace("__", "."): torch.from_numpy(np.asarray(v, dtype=np.float32)) for k, v in g.items() if k.startswith("sd_")})
+        m = m.cuda()
+        m.fuse_prologue = fused
+        q = _dev(g["query"], torch.float32).requires_grad_(True)
+        src = _dev(g["src"], torch.float32).requires_grad_(True)
+        y = m(q, _dev(g["ref2"], torch.float32), src, _dev(g["shapes"]), _dev(g["start"]), _dev(g["mask"]))
+        assert pkg.last_variant("forward") == ("slab32+prologue" if fused else "slab32")
+        (y * _dev(g["wout"], torch.float32)).sum().backward()
+        torch.cuda.synchronize()
+        got = dict(y=y, grad_query=q.grad, grad_src=src.grad, grad_offsets_bias=m.sampling_offsets.bias.grad,
+                   grad_attn_bias=m.attention_weights.bias.grad, grad_value_bias=m.value_proj.bias.grad,
+                   grad_offsets_weight_rowsum=m.sampling_offsets.weight.grad.sum(1), grad_attn_weight_rowsum=m.attention_weights.weight.grad.sum(1))
+        for k, t in got.items():
+            tol = FWD_TOL[torch.float32] * 10 if k == "y" else BWD_TOL[torch.float32] * 10  # fp32 GEMMs around the op
+            assert rel_err(t.detach().cpu().numpy(), g[k]) < tol, (fused, k, rel_err(t.detach().cpu().numpy(), g[k]))
+        results[fused] = got
+    for k in results[True]:
+        assert rel_err(results[True][k].detach().cpu().numpy(), results[False][k].detach().cpu().numpy()) < 1e-4, k
+
+
+def test_fused_prologue_falls_back_when_it_does_not_apply(pkg):
+    """4-d reference points, reference points that need a gradient and float64 take the reference's composition."""
+    g = load_golden("module_small")
+    m = pkg.MSDeformAttn(d_model=32, n_levels=3, n_heads=2, n_points=4).double()
+    m.load_state_dict({k[3:].replace("__", "."): torch.from_numpy(v) for k, v in g.items() if k.startswith("sd_")})
+    m = m.cuda()
+    y4 = m(_dev(g["query"]), _dev(g["ref4"]), _dev(g["src"]), _dev(g["shapes"]), _dev(g["start"]), None)
+    assert pkg.last_variant("forward") != "slab32+prologue"
+    assert rel_err(y4.detach().cpu().numpy(), g["y4"]) < 1e-12
+    g2 = load_golden("module_d256")
+    m = pkg.MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4).cuda()
+    ref = _dev(g2["ref2"], torch.float32).requires_grad_(True)
+    y = m(_dev(g2["query"], torch.float32), ref, _dev(g2["src"], torch.float32), _dev(g2["shapes"]), _dev(g2["start"]), None)
+    assert pkg.last_variant("forward") == "slab32"
+    y.sum().backward()
+    assert ref.grad is not None and torch.isfinite(ref.grad).all()
