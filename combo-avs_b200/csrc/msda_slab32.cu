@@ -34,6 +34,7 @@ struct SlabParams {
     unsigned wrecip[kMaxLevels];  // ceil(2^32 / W): pixel / W == umulhi(pixel, wrecip) for pixel < 2^16
     unsigned precip;          // ceil(2^32 / (3*L*P/4)) for the metadata staging index split
     int padded_rows;          // total rows of the padded slab
+    int wstage;               // every warp stages its own rows' metadata: the per-pass CTA barrier becomes a warp barrier
     int fused;                // loc = raw offsets, attn = raw logits: transform the staged rows in place (needs STAGE)
     int qpp;                  // queries per pass
     int pps;                  // passes per slab
@@ -158,25 +159,36 @@ __device__ __forceinline__ void floor_split(float x, float &fl, int &i)
 template <typename TM>
 __device__ __forceinline__ void stage_meta(TM *meta, const TM *__restrict__ loc, const TM *__restrict__ attn,
                                            const SlabParams &sp, int LP, long long nm, int q0, int cnt,
-                                           TM *refs = nullptr, const TM *__restrict__ ref = nullptr)
+                                           TM *refs, const TM *__restrict__ ref, int rows_per_warp)
 {
     const long long n = nm / sp.M;
     const int m = (int)(nm - n * sp.M);
     const int pieces = (3 * LP) >> 2, loc_pieces = LP >> 1;  // pieces of 4 elements (16 bytes of fp32, 8 bytes of bf16)
-    const int total = cnt * pieces;
-    const long long qm0 = (n * sp.Lq + q0) * sp.M + m;
+    // rows_per_warp > 0: every warp stages only the rows its own lanes will read (no CTA barrier needed per pass);
+    // rows_per_warp == 0: the whole CTA stages the whole pass
+    int r0 = 0, nrows = cnt, t = threadIdx.x, nt = blockDim.x;
+    if (rows_per_warp > 0) {
+        r0 = (threadIdx.x >> 5) * rows_per_warp;
+        nrows = min(max(cnt - r0, 0), rows_per_warp);
+        t = threadIdx.x & 31;
+        nt = 32;
+    }
+    const int total = nrows * pieces;
+    const long long qm0 = (n * sp.Lq + q0 + r0) * sp.M + m;
     const TM *lbase = loc + qm0 * (2 * LP), *abase = attn + qm0 * LP;
     const int lstride = sp.M * 2 * LP, astride = sp.M * LP;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    TM *mrow = meta + r0 * (3 * LP);
+    for (int i = t; i < total; i += nt) {
         const int ql = (int)__umulhi((unsigned)i, sp.precip), pc = i - ql * pieces;
         const TM *src = pc < loc_pieces ? lbase + ql * lstride + pc * 4 : abase + ql * astride + (pc - loc_pieces) * 4;
-        if (sizeof(TM) == 4) cp_async16(meta + ql * (3 * LP) + pc * 4, src);
-        else cp_async8(meta + ql * (3 * LP) + pc * 4, src);
+        if (sizeof(TM) == 4) cp_async16(mrow + ql * (3 * LP) + pc * 4, src);
+        else cp_async8(mrow + ql * (3 * LP) + pc * 4, src);
     }
-    if (refs != nullptr) {  // fused prologue: the pass's reference points, [cnt][L][2] contiguous in global memory
-        const TM *rsrc = ref + ((n * sp.Lq + q0) * sp.L) * 2;
-        for (int i = threadIdx.x; i < cnt * sp.L; i += blockDim.x) {
-            const unsigned d = (unsigned)__cvta_generic_to_shared(refs + i * 2);
+    if (refs != nullptr) {  // fused prologue: the rows' reference points, [rows][L][2] contiguous in global memory
+        const TM *rsrc = ref + ((n * sp.Lq + q0 + r0) * sp.L) * 2;
+        TM *rdst = refs + r0 * sp.L * 2;
+        for (int i = t; i < nrows * sp.L; i += nt) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(rdst + i * 2);
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(rsrc + i * 2) : "memory");
         }
     }
@@ -211,6 +223,7 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
     TM *refs0 = meta0 + 2 * meta_stride;
     const int ref_stride = sp.qpp * sp.L * 2;
     const bool fused = STAGE && sizeof(TM) == 4 && sp.fused != 0;
+    const int rpw = sp.wstage ? 32 / SPLIT : 0;  // (query, head) rows per warp
     for (int l = 0; l < sp.L; ++l) {  // zero the one-pixel border of every level once; slab loads only ever write interiors
         const int H = sp.H[l], Wp = sp.W[l] + 2;
         float4 *lv = slab + (size_t)sp.prow0[l] * 8;
@@ -248,15 +261,18 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
     if (STAGE && u_lo < u_hi) {
         long long nm; int q0, cnt;
         pass_range(u_lo, nm, q0, cnt);
-        stage_meta(meta0, loc, attn, sp, LP, nm, q0, cnt, fused ? refs0 : nullptr, ref);
+        stage_meta(meta0, loc, attn, sp, LP, nm, q0, cnt, fused ? refs0 : nullptr, ref, rpw);
     }
     for (long long u = u_lo; u < u_hi; ++u) {
         long long nm; int q0, cnt;
         pass_range(u, nm, q0, cnt);
         const TM *meta = meta0 + ((u - u_lo) & 1) * meta_stride;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();  // staged metadata visible; everyone is done with the previous pass (and the zero fill)
         const bool fresh = nm != resident;  // a new slab: its levels arrive as separate cp.async groups
+        // staged metadata visible.  A new slab (and the first pass, after the zero fill) needs the whole CTA to have left the
+        // previous pass; with warp-private staging a pass on the resident slab only needs the warp itself.
+        if (fresh || rpw == 0) __syncthreads();
+        else __syncwarp();
         if (fresh) {
             load_slab(slab, value, sp, nm);
             resident = nm;
@@ -266,7 +282,7 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
                 long long nm2; int q02, cnt2;
                 pass_range(u + 1, nm2, q02, cnt2);
                 stage_meta(meta0 + ((u + 1 - u_lo) & 1) * meta_stride, loc, attn, sp, LP, nm2, q02, cnt2,
-                           fused ? refs0 + ((u + 1 - u_lo) & 1) * ref_stride : nullptr, ref);
+                           fused ? refs0 + ((u + 1 - u_lo) & 1) * ref_stride : nullptr, ref, rpw);
             } else {
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
@@ -309,7 +325,8 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
                     }
                 }
             }
-            __syncthreads();  // both lanes of a pair read the whole row below
+            if (rpw == 0) __syncthreads();  // both lanes of a pair read the whole row below
+            else __syncwarp();
         }
         f4p acc[CH];
 #pragma unroll
@@ -391,6 +408,12 @@ int slab_split()
     return v;
 }
 
+bool slab_wstage()
+{
+    static const bool v = [] { const char *e = getenv("MSDA_SLAB_WSTAGE"); return !(e && atoi(e) == 0); }();
+    return v;
+}
+
 bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &threads, int &grid, bool &stage)
 {
     const int split = slab_split();
@@ -426,6 +449,7 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
     const size_t meta_bytes = 2 * (size_t)sp.qpp * 3 * LP * (p.loc_dtype == 1 ? 2 : 4);
     stage = (LP % 4 == 0) && smem_bytes + meta_bytes <= (size_t)p.smem_optin;
     if (stage) smem_bytes += meta_bytes;
+    sp.wstage = (stage && slab_wstage()) ? 1 : 0;
     sp.fused = 0;
     if (p.ref != nullptr) {  // fused prologue: needs the staged path, float32 metadata and room for the reference points
         const size_t ref_bytes = 2 * (size_t)sp.qpp * p.L * 2 * 4;

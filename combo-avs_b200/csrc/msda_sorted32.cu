@@ -124,7 +124,7 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
     float4 *ent = smem4 + (size_t)sp.vrows_max * 8;       // sorted samples: {lh, lw, attn, cell<<20 | p<<16 | q}
     int *cell_off = reinterpret_cast<int *>(ent + EP);    // kMaxCells + 1 counters -> exclusive offsets
     int *warp_tot = cell_off + kMaxCells + 8;
-    constexpr bool GRING = (MODE & 1) != 0, DEFER = (MODE & 2) != 0;
+    constexpr bool GRING = (MODE & 1) != 0, DEFER = (MODE & 2) != 0, FUSED = (MODE & 4) != 0;
     // GRING: slot (stage, k) of thread t at gring + ((stage*CH + k) * kThreads + t) * 16 bytes, three stages
     unsigned gslot_s = (unsigned)__cvta_generic_to_shared(warp_tot + 32) + threadIdx.x * 16;
     pin(gslot_s);
@@ -178,7 +178,7 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
             if (i < EP) {
                 const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
                 float2 xy = load2(locb + 2 * (q * qstride + p));
-                if (sp.fused) {  // module prologue (ms_deform_attn.py:110-112): reference point + offset / (W_l, H_l)
+                if (FUSED) {  // module prologue (ms_deform_attn.py:110-112): reference point + offset / (W_l, H_l)
                     const float2 rf = load2(ref + ((n * Lq + q) * sp.L + l) * 2);
                     xy.x = __fadd_rn(rf.x, __fdiv_rn(xy.x, Wf));
                     xy.y = __fadd_rn(rf.y, __fdiv_rn(xy.y, Hf));
@@ -344,7 +344,7 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         TM *res_base = SPLIT >= 4 ? (j == 0 ? gatt : gloc + (j == 1 ? 1 : 0)) : (j == 0 ? gloc : gatt);
         int res_stride = SPLIT >= 4 ? (j == 0 ? 1 : 2) : (j == 0 ? 2 : 1);
         // d(loc)/d(offset) = 1 / (W, H) cancels the (W, H) factor of grad_sampling_loc (cuh:126-127) in the fused form
-        float res_scale = (j == 0 || sp.fused) ? 1.f : (j == 1 ? Hf : Wf);
+        float res_scale = (j == 0 || FUSED) ? 1.f : (j == 1 ? Hf : Wf);
         pin(res_base); pin(res_stride); pin(res_scale); pin(gobase); pin(gbase);
         int cur = -1, inmask = 0;
         float *gp = gbase;             // grad_value row of the current cell's top-left neighbour
@@ -471,7 +471,7 @@ _Pragma("unroll") \
                 s_h += __shfl_xor_sync(0xffffffffu, s_h, 1); \
                 s_w += __shfl_xor_sync(0xffffffffu, s_w, 1); \
                 if (active) { \
-                    if (j == 0) store2(res_base + sidx * 2, (sp.fused ? 1.f : Wf) * att_v * s_w, (sp.fused ? 1.f : Hf) * att_v * s_h); \
+                    if (j == 0) store2(res_base + sidx * 2, (FUSED ? 1.f : Wf) * att_v * s_w, (FUSED ? 1.f : Hf) * att_v * s_h); \
                     else store1(res_base + sidx, s_a); \
                 } \
             } else if (DEFER) { \
@@ -594,6 +594,7 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
     sp.prefetch = sorted_prefetch() ? 1 : 0;
     sp.fused = p.ref != nullptr ? 1 : 0;
     if (sp.fused && p.loc_dtype != 0) return false;
+    if (sp.fused) mode = 0;
     return true;
 }
 
@@ -607,6 +608,7 @@ cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc,
     };
     auto pick_mode = [&](auto pt) {
         using std::integral_constant;
+        if (sp.fused) return pick(pt, integral_constant<int, 4>());  // fused prologue: plain register pipeline
         return mode == 3 ? pick(pt, integral_constant<int, 3>()) : mode == 2 ? pick(pt, integral_constant<int, 2>())
              : mode == 1 ? pick(pt, integral_constant<int, 1>()) : pick(pt, integral_constant<int, 0>());
     };
