@@ -80,9 +80,9 @@ def load():
     lib.msda_forward_backward_host.restype = i
     lib.msda_fused_supported.argtypes = [i, i, i, i, i, i, i, i, ip, ip, i]
     lib.msda_fused_supported.restype = i
-    lib.msda_fused_forward.argtypes = [i, vp, ip, ip, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, ip, ip, i, vp]
+    lib.msda_fused_forward.argtypes = [i, vp, ip, ip, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, ip, ip, i, vp]
     lib.msda_fused_forward.restype = i
-    lib.msda_fused_backward.argtypes = [i, vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, ip, ip, i, vp]
+    lib.msda_fused_backward.argtypes = [i, vp, ip, ip, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, ip, ip, i, vp]
     lib.msda_fused_backward.restype = i
     _lib = lib
     return lib

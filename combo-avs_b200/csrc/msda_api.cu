@@ -296,8 +296,8 @@ int msda_fused_supported(int dtype, int N, int S, int M, int D, int L, int Lq, i
 }
 
 int msda_fused_forward(int dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                       const void *reference_points, const void *sampling_offsets, const void *attention_logits, void *output,
-                       void *attention_weights_out, int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
+                       const void *reference_points, const void *sampling_offsets, const void *attention_logits,
+                       const unsigned char *padding_mask, void *output, void *attention_weights_out, int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
                        const int64_t *shapes_host, const int64_t *level_start_host, int device, void *stream)
 {
     Problem p;
@@ -308,6 +308,7 @@ int msda_fused_forward(int dtype, const void *value, const int64_t *spatial_shap
     if (!output || !reference_points || !attention_weights_out) return fail(MSDA_ERR_NULL, "NULL pointer in fused forward");
     p.ref = reference_points;
     p.attn_out = attention_weights_out;
+    p.mask = padding_mask;
     if (dtype != MSDA_F32 || !slab32_supported(p))
         return fail(MSDA_ERR_VARIANT, "fused forward needs f32, D=32, L*P %% 4 == 0, host geometry and a padded slab that fits shared memory");
     DeviceGuard guard;
@@ -321,7 +322,7 @@ int msda_fused_forward(int dtype, const void *value, const int64_t *spatial_shap
 
 int msda_fused_backward(int dtype, const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                         const void *reference_points, const void *sampling_offsets, const void *attention_weights,
-                        const void *grad_output, void *grad_value, void *grad_sampling_offsets, void *grad_attention_logits, int N,
+                        const unsigned char *padding_mask, const void *grad_output, void *grad_value, void *grad_sampling_offsets, void *grad_attention_logits, int N,
                         int S, int M, int D, int L, int Lq, int P, int im2col_step, const int64_t *shapes_host,
                         const int64_t *level_start_host, int device, void *stream)
 {
@@ -344,6 +345,7 @@ int msda_fused_backward(int dtype, const void *value, const int64_t *spatial_sha
     if (!grad_output || !grad_sampling_offsets || !grad_attention_logits || !reference_points || (n_val > 0 && !grad_value))
         return fail(MSDA_ERR_NULL, "NULL pointer in fused backward");
     p.ref = reference_points;
+    p.mask = padding_mask;
     if (dtype != MSDA_F32 || !sorted32_supported(p))
         return fail(MSDA_ERR_VARIANT, "fused backward needs f32, D=32, host geometry, Lq*P <= 4608, (H+1)*(W+1) <= 1024 per level");
     // the sorted backward leaves d(out)/d(softmaxed weight) in grad_attention_logits; the softmax backward then runs in place
@@ -351,6 +353,7 @@ int msda_fused_backward(int dtype, const void *value, const int64_t *spatial_sha
     e = bwd_sorted32(p, io, st);
     if (e == cudaSuccess)
         e = softmax_backward_rows((const float *)attention_weights, (float *)grad_attention_logits, (long long)N * Lq * M, L * P, p.sm_count, st);
+    if (e == cudaSuccess && padding_mask) e = zero_masked_rows((float *)grad_value, padding_mask, (long long)N * S, M * D, p.sm_count, st);
     g_last_variant[1].store("sorted32+prologue");
     if (e != cudaSuccess) return cuda_fail(e, "msda_fused_backward launch");
     return MSDA_OK;

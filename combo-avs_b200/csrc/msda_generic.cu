@@ -232,6 +232,27 @@ __global__ void softmax_backward_kernel(const float *__restrict__ attn, float *_
 }
 }  // namespace
 
+namespace {
+__global__ void zero_masked_rows_kernel(float4 *__restrict__ grad, const unsigned char *__restrict__ mask, long long rows, int row_vec4)
+{
+    // one warp per row: the mask byte is read once; nothing is written for unmasked rows
+    const int lane = threadIdx.x & 31;
+    for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; r < rows; r += ((long long)gridDim.x * blockDim.x) >> 5) {
+        if (mask[r] == 0) continue;
+        for (int i = lane; i < row_vec4; i += 32) grad[r * row_vec4 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+}  // namespace
+
+cudaError_t zero_masked_rows(float *grad, const unsigned char *mask, long long rows, int row_elems, int sm_count, cudaStream_t st)
+{
+    if (rows <= 0 || !mask) return cudaSuccess;
+    if (row_elems % 4 != 0) return cudaErrorInvalidValue;
+    zero_masked_rows_kernel<<<sm_count * 4, 256, 0, st>>>(reinterpret_cast<float4 *>(grad), mask, rows, row_elems / 4);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t softmax_backward_rows(const float *attn, float *grad, long long rows, int LP, int sm_count, cudaStream_t st)
 {
     if (rows <= 0) return cudaSuccess;

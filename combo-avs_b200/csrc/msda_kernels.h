@@ -26,6 +26,7 @@ struct Problem {
     // taken in the kernel and written to `attn_out`), in the backward it holds the softmaxed weights saved by the forward.
     const void *ref = nullptr;   // [N, Lq, L, 2] (x, y), dtype of loc
     void *attn_out = nullptr;    // [N, Lq, M, L, P]
+    const unsigned char *mask = nullptr;  // optional padding mask [N, S] (non-zero = padded pixel: its value row reads as zero)
 };
 
 struct BackwardIO {
@@ -63,6 +64,8 @@ bool pipe32_supported(const Problem &p);
 size_t bwd_pipe32_workspace(int dtype, int D, int Lq, int P);
 cudaError_t bwd_pipe32(const Problem &p, const BackwardIO &io, cudaStream_t st);
 
+// zero the rows of grad[rows][row_elems] whose mask byte is set (masked_fill backward, ms_deform_attn.py:103-104)
+cudaError_t zero_masked_rows(float *grad, const unsigned char *mask, long long rows, int row_elems, int sm_count, cudaStream_t st);
 // softmax backward over the last L*P entries of every (frame, query, head) row, in place on grad (msda_generic.cu)
 cudaError_t softmax_backward_rows(const float *attn, float *grad, long long rows, int LP, int sm_count, cudaStream_t st);
 

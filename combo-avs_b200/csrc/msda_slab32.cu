@@ -211,7 +211,8 @@ __device__ __forceinline__ void pin(unsigned &x) { asm volatile("" : "+r"(x)); }
 template <typename TV, typename TM, int P_T, bool STAGE, int SPLIT>
 __global__ void __launch_bounds__(SPLIT == 4 ? 768 : 512, 1)
 fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, const TM *__restrict__ attn,
-                  TV *__restrict__ out, const TM *__restrict__ ref, TM *__restrict__ attn_out, const __grid_constant__ SlabParams sp)
+                  TV *__restrict__ out, const TM *__restrict__ ref, TM *__restrict__ attn_out, const unsigned char *__restrict__ mask,
+                  const __grid_constant__ SlabParams sp)
 {
     constexpr int CH = 8 / SPLIT;  // 16-byte chunks (4 channels) per lane
     extern __shared__ float4 slab[];
@@ -335,6 +336,20 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
             if (fresh) {  // level l of the new slab must have landed (levels after it and the metadata group may still be in flight)
                 cp_async_wait_pending(sp.L - 1 - l + (STAGE ? 1 : 0));
                 __syncthreads();
+                if (fused && mask != nullptr) {  // padding mask folded in (ms_deform_attn.py:103-104): masked pixels read as zero rows
+                    const int W = sp.W[l], npix = sp.H[l] * W;
+                    const unsigned char *mk = mask + (nm / sp.M) * sp.S + sp.start[l];
+                    float4 *lv = slab + (size_t)(sp.prow0[l] + (W + 2) + 1) * 8;
+                    for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
+                        if (mk[pix]) {
+                            const int y = (int)__umulhi((unsigned)pix, sp.wrecip[l]), x = pix - y * W;
+                            float4 *row = lv + (size_t)(y * (W + 2) + x) * 8;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) row[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    __syncthreads();
+                }
             }
             if (!live) continue;
             const float Hf = (float)sp.H[l], Wf = (float)sp.W[l];
@@ -470,7 +485,7 @@ cudaError_t launch_typed(const Problem &p, void *out, cudaStream_t st, const Sla
                                   : (s4 ? fwd_slab32_kernel<TV, TM, 0, false, 4> : fwd_slab32_kernel<TV, TM, 0, false, 2>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, threads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (TV *)out, (const TM *)p.ref, (TM *)p.attn_out, sp);
+    kern<<<grid, threads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (TV *)out, (const TM *)p.ref, (TM *)p.attn_out, p.mask, sp);
     count_launch();
     return cudaGetLastError();
 }

@@ -113,7 +113,8 @@ template <typename TV, typename TM, int P_T, int SPLIT, int MODE>
 __global__ void __launch_bounds__(threads_for_split(SPLIT), 1)
 bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, const TM *__restrict__ attn,
                     const TV *__restrict__ grad_out, float *__restrict__ grad_value, TM *__restrict__ grad_loc,
-                    TM *__restrict__ grad_attn, const TM *__restrict__ ref, const __grid_constant__ SortParams sp)
+                    TM *__restrict__ grad_attn, const TM *__restrict__ ref, const unsigned char *__restrict__ mask,
+                    const __grid_constant__ SortParams sp)
 {
     constexpr int kThreads = threads_for_split(SPLIT), CH = 8 / SPLIT;
     constexpr int kGroups = kThreads / SPLIT, kRounds = (kMaxSamples + kThreads - 1) / kThreads;
@@ -292,6 +293,17 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (FUSED && mask != nullptr) {  // padding mask folded in: masked pixels read as zero rows (their grad_value is zeroed afterwards)
+            __syncthreads();
+            const unsigned char *mk = mask + n * sp.S + sp.start[l];
+            for (int pxl = tid; pxl < H * W; pxl += kThreads) {
+                if (mk[pxl]) {
+                    const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) V4[((y + 1) * Wp + x + 1) * 8 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
         __syncthreads();  // sorted list complete, value slab landed
 
         // ---- L2 prefetch of the next whole unit of this CTA: its locations / weights, its value rows and, when it starts a new
@@ -623,7 +635,7 @@ cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc,
     if (sp.parts > 4) sp.parts = 4;
     if (sp.parts < 1) sp.parts = 1;
     kern<<<grid, kThreads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (const TV *)io.grad_out, gv_acc,
-                                       (TM *)io.grad_loc, (TM *)io.grad_attn, (const TM *)p.ref, sp);
+                                       (TM *)io.grad_loc, (TM *)io.grad_attn, (const TM *)p.ref, p.mask, sp);
     count_launch();
     return cudaGetLastError();
 }

@@ -169,10 +169,12 @@ class MSDeformAttnPrologueFunction(Function):
     apply(value[N,S,M,D], spatial_shapes, level_start_index, reference_points[N,Lq,L,2], sampling_offsets[N,Lq,M,L,P,2],
           attention_logits[N,Lq,M,L*P], im2col_step) == MSDeformAttnFunction.apply(value, shapes, start,
           reference_points[:, :, None, :, None, :] + sampling_offsets / (W_l, H_l), softmax(attention_logits, -1), im2col_step).
-    backward returns (grad_value, None, None, None, grad_sampling_offsets, grad_attention_logits, None)."""
+    An optional trailing padding_mask [N, S] (bool) stands for value.masked_fill(mask[..., None], 0) before the op.
+    backward returns (grad_value, None, None, None, grad_sampling_offsets, grad_attention_logits, None, None)."""
 
     @staticmethod
-    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits, im2col_step):
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attention_logits, im2col_step,
+                padding_mask=None):
         named = (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                  ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attention_logits", attention_logits))
         _check_inputs(named, value)
@@ -185,6 +187,11 @@ class MSDeformAttnPrologueFunction(Function):
                                (tuple(value.shape), tuple(reference_points.shape), tuple(sampling_offsets.shape), tuple(attention_logits.shape)))
         if not (value.dtype == sampling_offsets.dtype == attention_logits.dtype == reference_points.dtype == torch.float32):
             raise RuntimeError("the fused prologue takes float32 tensors")
+        if padding_mask is not None:
+            # replaces value.masked_fill(mask[..., None], 0) of the module (ms_deform_attn.py:103-104): `value` comes in unmasked
+            if padding_mask.dtype != torch.bool or tuple(padding_mask.shape) != (N, S) or padding_mask.device != value.device:
+                raise RuntimeError("padding_mask must be a bool tensor of shape [N, S] on the device of value")
+            padding_mask = padding_mask.contiguous()
         ctx.im2col_step = im2col_step
         ctx.geometry = _host_geometry(spatial_shapes, level_start_index)
         hs, hl = ctx.geometry[:2]
@@ -193,10 +200,11 @@ class MSDeformAttnPrologueFunction(Function):
         dev = value.device.index if value.device.index is not None else torch.cuda.current_device()
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = _lib.load().msda_fused_forward(_lib.F32, _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(reference_points),
-                                            _ptr(sampling_offsets), _ptr(attention_logits), _ptr(out), _ptr(attn), N, S, M, D, L, Lq, P,
+                                            _ptr(sampling_offsets), _ptr(attention_logits), _ptr(padding_mask), _ptr(out), _ptr(attn), N, S, M, D, L, Lq, P,
                                             int(im2col_step), hs, hl, dev, ctypes.c_void_p(stream))
         _lib.check(rc)
         ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn)
+        ctx.padding_mask = padding_mask
         ctx.logits_shape = attention_logits.shape
         return out
 
@@ -215,8 +223,8 @@ class MSDeformAttnPrologueFunction(Function):
         dev = value.device.index if value.device.index is not None else torch.cuda.current_device()
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = _lib.load().msda_fused_backward(_lib.F32, _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(reference_points),
-                                             _ptr(sampling_offsets), _ptr(attn), _ptr(grad_output), _ptr(grad_value), _ptr(grad_off),
+                                             _ptr(sampling_offsets), _ptr(attn), _ptr(ctx.padding_mask), _ptr(grad_output), _ptr(grad_value), _ptr(grad_off),
                                              _ptr(grad_logits), N, S, M, D, L, Lq, P, int(ctx.im2col_step), hs, hl, dev,
                                              ctypes.c_void_p(stream))
         _lib.check(rc)
-        return grad_value, None, None, None, grad_off, grad_logits, None
+        return grad_value, None, None, None, grad_off, grad_logits, None, None

@@ -75,18 +75,19 @@ class MSDeformAttn(nn.Module):
         N, Len_in, _ = input_flatten.shape
         assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
-        value = self.value_proj(input_flatten)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], float(0))
-        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        value = self.value_proj(input_flatten).view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         sampling_offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         attention_weights = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
-        if self.fuse_prologue and fused_prologue_supported(value, input_spatial_shapes, input_level_start_index, reference_points, sampling_offsets):
+        if self.fuse_prologue and fused_prologue_supported(value, input_spatial_shapes, input_level_start_index, reference_points, sampling_offsets) \
+                and (input_padding_mask is None or input_padding_mask.dtype == torch.bool):
+            # softmax, location arithmetic and the padding mask happen inside the kernels (include/msda_b200.h: msda_fused_*)
             output = MSDeformAttnPrologueFunction.apply(value, input_spatial_shapes, input_level_start_index, reference_points.contiguous(),
-                                                        sampling_offsets, attention_weights, self.im2col_step)
+                                                        sampling_offsets, attention_weights, self.im2col_step, input_padding_mask)
             return self.output_proj(output)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None, None], float(0))
         attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
         if reference_points.shape[-1] == 2:
             offset_normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)

@@ -117,6 +117,9 @@ int msda_version(void);
  * once (attention_weights_out, needed by the backward); the backward rebuilds the locations while it sorts, writes
  * d/d(sampling_offsets) directly (the (W, H) factors of ms_deform_im2col_cuda.cuh:126-127 cancel) and finishes with an
  * in-place softmax backward, so grad_attention_logits is d/d(logits).  reference_points: [N, Lq, L, 2] (x, y), no gradient.
+ * padding_mask (optional, NULL = none): [N, S] bytes, non-zero = padded pixel.  It replaces the module's
+ * value.masked_fill(mask, 0) (ms_deform_attn.py:103-104) and its backward: masked pixels read as zero rows while the slab is
+ * staged, and their grad_value rows are zeroed at the end, so `value` is passed unmasked.
  * float32, D = 32, host geometry required; msda_fused_supported() tells whether a shape qualifies (else compose the unfused
  * entry points as the reference does).  Everything else (layouts, statuses, stream / device) as msda_forward / msda_backward.
  */
@@ -125,12 +128,13 @@ int msda_fused_supported(int dtype, int N, int S, int M, int D, int L, int Lq, i
 int msda_fused_forward(int dtype,
                        const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                        const void *reference_points, const void *sampling_offsets, const void *attention_logits,
-                       void *output, void *attention_weights_out,
+                       const unsigned char *padding_mask, void *output, void *attention_weights_out,
                        int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
                        const int64_t *shapes_host, const int64_t *level_start_host, int device, void *stream);
 int msda_fused_backward(int dtype,
                         const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                         const void *reference_points, const void *sampling_offsets, const void *attention_weights,
+                        const unsigned char *padding_mask,
                         const void *grad_output, void *grad_value, void *grad_sampling_offsets, void *grad_attention_logits,
                         int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
                         const int64_t *shapes_host, const int64_t *level_start_host, int device, void *stream);

@@ -436,6 +436,37 @@ def test_fused_prologue_function_matches_oracle(pkg, N, spread):
     assert rel_err(out.detach().cpu().numpy(), out2.cpu().numpy()) < 2e-6
 
 
+def test_fused_prologue_padding_mask(pkg):
+    """padding_mask folded into the kernels == value.masked_fill(mask, 0) before the op, forward and all gradients."""
+    from combo_avs_b200.functions import MSDeformAttnPrologueFunction
+    N, L, P, M, Lq = 3, 3, 4, 8, 1029
+    rng = np.random.default_rng(77)
+    d = make_inputs(N, S4_SHAPES, 8, 32, Lq, 4, seed=78)
+    off = (rng.standard_normal((N, Lq, M, L, P, 2)) * 3).astype(np.float32)
+    logits = rng.standard_normal((N, Lq, M, L * P)).astype(np.float32)
+    ref = rng.random((N, Lq, L, 2)).astype(np.float32)
+    mask = rng.random((N, d["value"].shape[1])) < 0.25
+    mask[1] = False   # one frame without padding, one fully padded
+    mask[2] = True
+    d64 = {k: (np.asarray(v, dtype=np.float64) if np.asarray(v).dtype.kind == "f" else v) for k, v in d.items()}
+    d64["value"] = np.where(mask[:, :, None, None], 0.0, d64["value"])
+    want = _prologue_reference(d64, off.astype(np.float64), logits.astype(np.float64), ref.astype(np.float64), d64["grad_out"])
+    want["grad_value"] = np.where(mask[:, :, None, None], 0.0, want["grad_value"])
+    v = _dev(d["value"]).requires_grad_(True)
+    o = _dev(off).requires_grad_(True)
+    lg = _dev(logits).requires_grad_(True)
+    out = MSDeformAttnPrologueFunction.apply(v, _dev(d["shapes"]), _dev(d["start"]), _dev(ref), o, lg, 128, torch.from_numpy(mask).cuda())
+    out.backward(_dev(d["grad_out"]))
+    torch.cuda.synchronize()
+    assert rel_err(out.detach().cpu().numpy(), want["out"]) < FWD_TOL[torch.float32]
+    assert float(out[2].abs().max()) == 0.0
+    gv = v.grad.cpu().numpy()
+    assert rel_err(gv, want["grad_value"]) < BWD_TOL[torch.float32]
+    assert np.all(gv[mask] == 0.0)
+    assert rel_err(lg.grad.cpu().numpy(), want["grad_logits"]) < BWD_TOL[torch.float32]
+    check_grad_loc(o.grad.cpu().numpy(), want["grad_off"], dict(d, loc=want["loc"].astype(np.float32)), BWD_TOL[torch.float32])
+
+
 def test_fused_module_matches_reference_module_d256(pkg):
     """The module at the production head width against the reference module's float64 run (tests/golden/module_d256.npz):
     fused and unfused paths, outputs and gradients (inputs, biases, weight row sums)."""
