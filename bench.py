@@ -201,6 +201,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=dev)
 
     import combo_avs_b200 as pkg
