@@ -1,0 +1,144 @@
+"""The caller of the hot path: the deformable-attention encoder of COMBO's pixel decoder.
+
+Drop-in equivalents (same constructor arguments, attribute / state-dict names and forward signatures) of
+    MSDeformAttnTransformerEncoderLayer   (/root/reference/models/modeling/pixel_decoder/msdeformattn.py:98-134)
+    MSDeformAttnTransformerEncoder        (:137-166)
+    MSDeformAttnTransformerEncoderOnly    (:23-95)
+built on this package's MSDeformAttn, so that the six encoder layers run the sm_100a kernels (with the fused prologue,
+functions.MSDeformAttnPrologueFunction, when it applies).  Everything around the op is plain PyTorch, as in the reference.
+Two host-side differences, neither visible in the numbers:
+  * the level geometry is built from Python ints and cached per shape tuple, and the reference points are computed from it
+    without iterating over a device tensor (the reference's loop at :146 syncs the stream once per level per call);
+  * the int64 geometry tensors are reused across calls, so the wrapper's host mirror of them (functions._host_geometry) hits.
+"""
+import copy
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .modules import MSDeformAttn
+
+_ACTIVATIONS = {"relu": F.relu, "gelu": F.gelu, "glu": F.glu}
+
+
+def _activation(name):
+    try:
+        return _ACTIVATIONS[name]
+    except KeyError:
+        raise RuntimeError("activation should be relu/gelu, not %s." % name) from None
+
+
+class MSDeformAttnTransformerEncoderLayer(nn.Module):
+    """Deformable self-attention + residual + LayerNorm, then FFN + residual + LayerNorm (msdeformattn.py:98-134)."""
+
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.activation = _activation(activation)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    @staticmethod
+    def with_pos_embed(tensor, pos):
+        return tensor if pos is None else tensor + pos
+
+    def forward_ffn(self, src):
+        hidden = self.dropout2(self.activation(self.linear1(src)))
+        return self.norm2(src + self.dropout3(self.linear2(hidden)))
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
+        attended = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes, level_start_index, padding_mask)
+        return self.forward_ffn(self.norm1(src + self.dropout1(attended)))
+
+
+class MSDeformAttnTransformerEncoder(nn.Module):
+    """A stack of independent copies of one encoder layer, all fed the same reference points (msdeformattn.py:137-166)."""
+
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
+        self.num_layers = num_layers
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        """Pixel centres of every level in normalised coordinates, rescaled by the valid ratios: [N, sum H*W, L, 2] (x, y).
+        spatial_shapes: a sequence of (H, W) Python ints or an int64 tensor (msdeformattn.py:143-157)."""
+        shapes = spatial_shapes.tolist() if torch.is_tensor(spatial_shapes) else [tuple(s) for s in spatial_shapes]
+        per_level = []
+        for lvl, (h, w) in enumerate(shapes):
+            ys = torch.linspace(0.5, h - 0.5, h, dtype=torch.float32, device=device)
+            xs = torch.linspace(0.5, w - 0.5, w, dtype=torch.float32, device=device)
+            gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+            x = gx.reshape(1, -1) / (valid_ratios[:, None, lvl, 0] * w)
+            y = gy.reshape(1, -1) / (valid_ratios[:, None, lvl, 1] * h)
+            per_level.append(torch.stack((x, y), -1))
+        points = torch.cat(per_level, 1)
+        return points[:, :, None] * valid_ratios[:, None]
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None, _shapes_host=None):
+        reference_points = self.get_reference_points(_shapes_host if _shapes_host is not None else spatial_shapes, valid_ratios, src.device)
+        output = src
+        for layer in self.layers:
+            output = layer(output, pos, reference_points, spatial_shapes, level_start_index, padding_mask)
+        return output
+
+
+class MSDeformAttnTransformerEncoderOnly(nn.Module):
+    """Flattens the multi-scale feature maps, adds the level embedding to the positional encoding and runs the encoder
+    (msdeformattn.py:23-95).  forward(srcs, pos_embeds) -> (memory [N, sum H*W, C], spatial_shapes, level_start_index)."""
+
+    def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.1, activation="relu",
+                 num_feature_levels=4, enc_n_points=4):
+        super().__init__()
+        self.d_model = d_model
+        self.nhead = nhead
+        layer = MSDeformAttnTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels, nhead, enc_n_points)
+        self.encoder = MSDeformAttnTransformerEncoder(layer, num_encoder_layers)
+        self.level_embed = nn.Parameter(torch.empty(num_feature_levels, d_model))
+        self._geometry = {}
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        nn.init.normal_(self.level_embed)
+
+    def get_valid_ratio(self, mask):
+        _, H, W = mask.shape
+        valid_h = (~mask[:, :, 0]).sum(1).float() / H
+        valid_w = (~mask[:, 0, :]).sum(1).float() / W
+        return torch.stack([valid_w, valid_h], -1)
+
+    def _level_geometry(self, shapes, device):
+        key = (shapes, str(device))
+        hit = self._geometry.get(key)
+        if hit is None:
+            spatial = torch.as_tensor(shapes, dtype=torch.long, device=device)
+            starts = [0]
+            for h, w in shapes[:-1]:
+                starts.append(starts[-1] + h * w)
+            hit = (spatial, torch.as_tensor(starts, dtype=torch.long, device=device))
+            self._geometry[key] = hit
+        return hit
+
+    def forward(self, srcs, pos_embeds):
+        shapes = tuple((int(x.shape[2]), int(x.shape[3])) for x in srcs)
+        batch, device = srcs[0].shape[0], srcs[0].device
+        tokens = torch.cat([x.flatten(2).transpose(1, 2) for x in srcs], 1)
+        positions = torch.cat([p.flatten(2).transpose(1, 2) + self.level_embed[lvl].view(1, 1, -1) for lvl, p in enumerate(pos_embeds)], 1)
+        # the decoder never pads (msdeformattn.py:68): an all-False mask, hence valid ratios of exactly one
+        mask = torch.zeros((batch, tokens.shape[1]), dtype=torch.bool, device=device)
+        valid_ratios = torch.ones((batch, len(shapes), 2), dtype=torch.float32, device=device)
+        spatial_shapes, level_start_index = self._level_geometry(shapes, device)
+        memory = self.encoder(tokens, spatial_shapes, level_start_index, valid_ratios, positions, mask, _shapes_host=shapes)
+        return memory, spatial_shapes, level_start_index

@@ -40,6 +40,37 @@ def import_reference():
     return ms_deform_attn_core_pytorch, MSDeformAttn
 
 
+def import_reference_encoder():
+    """The reference's encoder classes (pixel_decoder/msdeformattn.py:23-166).  The file imports detectron2 / fvcore at the
+    top for the pixel-decoder class further down; those names are stubbed (the encoder classes only use torch), and the two
+    sibling packages are registered as bare namespace packages so that their __init__ files (which pull in the whole model)
+    do not run."""
+    import importlib
+    root = "/root/reference/models/modeling"
+    def pkg(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+    pkg("refmodeling", root)
+    pkg("refmodeling.pixel_decoder", root + "/pixel_decoder")
+    pkg("refmodeling.transformer_decoder", root + "/transformer_decoder")
+    pkg("refmodeling.pixel_decoder.ops", root + "/pixel_decoder/ops")
+    import_reference()  # registers the extension stub
+    for name, attrs in (("fvcore", {}), ("fvcore.nn", {}), ("fvcore.nn.weight_init", {}),
+                        ("detectron2", {}), ("detectron2.config", {"configurable": lambda f: f}),
+                        ("detectron2.layers", {"Conv2d": object, "ShapeSpec": object, "get_norm": None}),
+                        ("detectron2.modeling", {"SEM_SEG_HEADS_REGISTRY": types.SimpleNamespace(register=lambda: (lambda c: c))})):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules.setdefault(name, m)
+    sys.modules["fvcore.nn"].weight_init = sys.modules["fvcore.nn.weight_init"]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = importlib.import_module("refmodeling.pixel_decoder.msdeformattn")
+    return mod.MSDeformAttnTransformerEncoderOnly
+
+
 def level_start(shapes):
     return torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
 
@@ -176,6 +207,30 @@ def main():
          grad_value_bias=mod.value_proj.bias.grad, grad_offsets_weight_rowsum=mod.sampling_offsets.weight.grad.sum(1),
          grad_attn_weight_rowsum=mod.attention_weights.weight.grad.sum(1),
          **{"sd_" + k.replace(".", "__"): v for k, v in state.items()})
+    # ---- the caller: one encoder layer stack of the pixel decoder (msdeformattn.py:23-166), reference classes, float64 -------
+    Enc = import_reference_encoder()
+    torch.manual_seed(13)
+    enc = Enc(d_model=256, nhead=8, num_encoder_layers=2, dim_feedforward=32, dropout=0.0, activation="relu",
+              num_feature_levels=3, enc_n_points=4)
+    with torch.no_grad():
+        for layer in enc.encoder.layers:  # the attention weights of module_d256 (stored there), small random FFN / norms
+            layer.self_attn.load_state_dict(state)
+            layer.norm1.weight.normal_(1, 0.1); layer.norm1.bias.normal_(0, 0.1)
+            layer.norm2.weight.normal_(1, 0.1); layer.norm2.bias.normal_(0, 0.1)
+    extra = {k: v.detach().clone() for k, v in enc.state_dict().items() if ".self_attn." not in k}
+    srcs = [torch.randn(1, 256, int(h), int(w)) for h, w in shapes.tolist()]
+    poss = [torch.randn(1, 256, int(h), int(w)) * 0.5 for h, w in shapes.tolist()]
+    wmem = torch.randn(1, S, 256)
+    enc = enc.double()
+    srcs_d = [x.double().requires_grad_(True) for x in srcs]
+    memory, shp_out, start_out = enc(srcs_d, [p.double() for p in poss])
+    (memory * wmem.double()).sum().backward()
+    save("encoder_d256", memory=memory.detach(), wmem=wmem, shapes_out=shp_out, start_out=start_out,
+         grad_level_embed=enc.level_embed.grad, grad_norm2_bias_l1=enc.encoder.layers[1].norm2.bias.grad,
+         grad_linear1_bias_l0=enc.encoder.layers[0].linear1.bias.grad,
+         **{"src%d" % i: x for i, x in enumerate(srcs)}, **{"pos%d" % i: x for i, x in enumerate(poss)},
+         **{"grad_src%d" % i: x.grad for i, x in enumerate(srcs_d)},
+         **{"sd_" + k.replace(".", "__"): v for k, v in extra.items()})
     fresh = MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4)
     save("module_init_256", offsets_bias=fresh.sampling_offsets.bias.detach(),
          offsets_weight_absmax=fresh.sampling_offsets.weight.detach().abs().max(),

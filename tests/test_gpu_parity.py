@@ -510,3 +510,36 @@ def test_fused_prologue_falls_back_when_it_does_not_apply(pkg):
     assert pkg.last_variant("forward") == "slab32"
     y.sum().backward()
     assert ref.grad is not None and torch.isfinite(ref.grad).all()
+
+
+# ------------------------------------------------------------------------------- the caller: pixel-decoder encoder (row a12)
+def test_encoder_matches_reference_encoder(pkg):
+    """MSDeformAttnTransformerEncoderOnly (two layers, d_model 256) against the reference's own classes run in float64
+    (tests/golden/encoder_d256.npz): memory and gradients, fused prologue on and off."""
+    from combo_avs_b200.encoder import MSDeformAttnTransformerEncoderOnly
+    g, gm = load_golden("encoder_d256"), load_golden("module_d256")
+    sd = {k[3:].replace("__", "."): torch.from_numpy(np.asarray(v, dtype=np.float32)) for k, v in g.items() if k.startswith("sd_")}
+    for i in range(2):
+        for k, v in gm.items():
+            if k.startswith("sd_"):
+                sd["encoder.layers.%d.self_attn.%s" % (i, k[3:].replace("__", "."))] = torch.from_numpy(np.asarray(v, dtype=np.float32))
+    for fused in (True, False):
+        enc = MSDeformAttnTransformerEncoderOnly(d_model=256, nhead=8, num_encoder_layers=2, dim_feedforward=32, dropout=0.0,
+                                                 num_feature_levels=3, enc_n_points=4)
+        enc.load_state_dict(sd)
+        enc = enc.cuda()
+        for layer in enc.encoder.layers:
+            layer.self_attn.fuse_prologue = fused
+        srcs = [_dev(g["src%d" % i], torch.float32).requires_grad_(True) for i in range(3)]
+        poss = [_dev(g["pos%d" % i], torch.float32) for i in range(3)]
+        memory, shapes, start = enc(srcs, poss)
+        assert pkg.last_variant("forward") == ("slab32+prologue" if fused else "slab32")
+        assert torch.equal(shapes.cpu(), torch.from_numpy(g["shapes_out"])) and torch.equal(start.cpu(), torch.from_numpy(g["start_out"]))
+        (memory * _dev(g["wmem"], torch.float32)).sum().backward()
+        torch.cuda.synchronize()
+        assert rel_err(memory.detach().cpu().numpy(), g["memory"]) < 1e-4
+        got = {"grad_level_embed": enc.level_embed.grad, "grad_norm2_bias_l1": enc.encoder.layers[1].norm2.bias.grad,
+               "grad_linear1_bias_l0": enc.encoder.layers[0].linear1.bias.grad}
+        got.update({"grad_src%d" % i: srcs[i].grad for i in range(3)})
+        for k, t in got.items():
+            assert rel_err(t.cpu().numpy(), g[k]) < 1e-3, (fused, k, rel_err(t.cpu().numpy(), g[k]))

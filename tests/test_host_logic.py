@@ -103,3 +103,22 @@ def test_reference_python_files_bind_to_the_shim(pkg):
         for k in [k for k in sys.modules if k == "MultiScaleDeformableAttention" or k == "ops" or k.startswith("ops.")]:
             sys.modules.pop(k)
         sys.modules.update(saved)
+
+
+def test_encoder_classes_mirror_reference_state_dict_and_reference_points(pkg):
+    """combo_avs_b200.encoder: parameter names equal the reference encoder's (golden file written by the reference classes),
+    and get_reference_points equals pixel centres / size (msdeformattn.py:143-157) for unit valid ratios."""
+    from combo_avs_b200.encoder import MSDeformAttnTransformerEncoder, MSDeformAttnTransformerEncoderOnly
+    g, gm = load_golden("encoder_d256"), load_golden("module_d256")
+    enc = MSDeformAttnTransformerEncoderOnly(d_model=256, nhead=8, num_encoder_layers=2, dim_feedforward=32, dropout=0.0,
+                                             num_feature_levels=3, enc_n_points=4)
+    want = {k[3:].replace("__", ".") for k in g if k.startswith("sd_")}
+    want |= {"encoder.layers.%d.self_attn.%s" % (i, k[3:].replace("__", ".")) for i in range(2) for k in gm if k.startswith("sd_")}
+    assert set(enc.state_dict().keys()) == want
+    shapes = [(2, 3), (4, 5)]
+    ref = MSDeformAttnTransformerEncoder.get_reference_points(shapes, torch.ones(2, 2, 2), "cpu")
+    assert ref.shape == (2, 26, 2, 2)
+    assert torch.allclose(ref[0, 0, 0], torch.tensor([0.5 / 3, 0.5 / 2])) and torch.allclose(ref[1, 6 + 7, 1], torch.tensor([2.5 / 5, 1.5 / 4]))
+    assert torch.equal(ref[:, :, 0], ref[:, :, 1])
+    t = MSDeformAttnTransformerEncoder.get_reference_points(torch.tensor(shapes), torch.ones(2, 2, 2), "cpu")
+    assert torch.equal(t, ref)
