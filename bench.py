@@ -22,6 +22,12 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: NCCL's banner ("NCCL version ..." under NCCL_DEBUG=VERSION/INFO) is written to stdout by
+# the library itself, so its debug output is pointed at stderr before torch / NCCL are loaded
+os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -201,7 +207,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL_DEBUG=VERSION prints there)
         dist.init_process_group("nccl", device_id=dev)
 
     import combo_avs_b200 as pkg

@@ -9,6 +9,9 @@ forces float anyway, msdeformattn.py:321).  Arms, same PyTorch code around the o
 Under torchrun (WORLD_SIZE > 1) the encoder is wrapped in DistributedDataParallel: one process per GPU, every rank its own
 frames (weak scaling), NCCL only for the gradient all-reduce.  Prints one JSON object (rank 0)."""
 import json, os, statistics, sys, time
+os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 import torch
 import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -46,7 +49,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     g = torch.Generator().manual_seed(100 + rank)
     srcs = [torch.randn(frames, 256, h, w, generator=g).to(dev) for h, w in S4]
