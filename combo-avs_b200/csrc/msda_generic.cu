@@ -235,11 +235,32 @@ __global__ void softmax_backward_kernel(const float *__restrict__ attn, float *_
 namespace {
 __global__ void zero_masked_rows_kernel(float4 *__restrict__ grad, const unsigned char *__restrict__ mask, long long rows, int row_vec4)
 {
-    // one warp per row: the mask byte is read once; nothing is written for unmasked rows
+    // a warp looks at 32 x 16 mask bytes per step (one 16-byte load per lane); only rows whose byte is set are written,
+    // by the whole warp -- for the decoder's all-False mask the kernel reads N*S bytes and writes nothing
     const int lane = threadIdx.x & 31;
-    for (long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; r < rows; r += ((long long)gridDim.x * blockDim.x) >> 5) {
-        if (mask[r] == 0) continue;
-        for (int i = lane; i < row_vec4; i += 32) grad[r * row_vec4 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp * 512; base < rows; base += nwarps * 512) {
+        const long long r0 = base + lane * 16;
+        uint4 m = make_uint4(0, 0, 0, 0);
+        if (r0 + 16 <= rows && ((reinterpret_cast<uintptr_t>(mask) + r0) & 15) == 0) {
+            m = *reinterpret_cast<const uint4 *>(mask + r0);
+        } else {
+            unsigned char *mb = reinterpret_cast<unsigned char *>(&m);
+            for (int i = 0; i < 16; ++i)
+                if (r0 + i < rows) mb[i] = mask[r0 + i];
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, (m.x | m.y | m.z | m.w) != 0);
+        for (unsigned todo = any; todo; todo &= todo - 1) {
+            const int src = __ffs(todo) - 1;
+            const unsigned w[4] = {__shfl_sync(0xffffffffu, m.x, src), __shfl_sync(0xffffffffu, m.y, src),
+                                   __shfl_sync(0xffffffffu, m.z, src), __shfl_sync(0xffffffffu, m.w, src)};
+            for (int i = 0; i < 16; ++i) {
+                if ((w[i >> 2] >> ((i & 3) * 8)) & 0xff) {
+                    const long long r = base + src * 16 + i;
+                    for (int c = lane; c < row_vec4; c += 32) grad[r * row_vec4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
     }
 }
 }  // namespace
@@ -248,7 +269,10 @@ cudaError_t zero_masked_rows(float *grad, const unsigned char *mask, long long r
 {
     if (rows <= 0 || !mask) return cudaSuccess;
     if (row_elems % 4 != 0) return cudaErrorInvalidValue;
-    zero_masked_rows_kernel<<<sm_count * 4, 256, 0, st>>>(reinterpret_cast<float4 *>(grad), mask, rows, row_elems / 4);
+    long long warps = (rows + 511) / 512;
+    long long blocks = (warps + 7) / 8;
+    if (blocks > sm_count * 8LL) blocks = sm_count * 8LL;
+    zero_masked_rows_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4 *>(grad), mask, rows, row_elems / 4);
     count_launch();
     return cudaGetLastError();
 }

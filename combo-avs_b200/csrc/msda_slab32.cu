@@ -31,6 +31,7 @@ struct SlabParams {
     int prow0[kMaxLevels];    // first padded row of the level inside the slab; padded pitch is W+2
     float hmax[kMaxLevels];   // largest float below H (clamp bound that leaves in-range samples untouched)
     float wmax[kMaxLevels];
+    float rw[kMaxLevels], rh[kMaxLevels];  // 1/W, 1/H (fused prologue)
     unsigned wrecip[kMaxLevels];  // ceil(2^32 / W): pixel / W == umulhi(pixel, wrecip) for pixel < 2^16
     unsigned precip;          // ceil(2^32 / (3*L*P/4)) for the metadata staging index split
     int padded_rows;          // total rows of the padded slab
@@ -297,32 +298,75 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
         const TM2 *loc2 = STAGE ? reinterpret_cast<const TM2 *>(meta + ql * 3 * LP) : reinterpret_cast<const TM2 *>(loc) + qm * LP;
         const TM *att = STAGE ? meta + ql * 3 * LP + 2 * LP : attn + qm * LP;
         if (fused) {
-            // Module prologue in place on the staged row of (query, head) (ops/modules/ms_deform_attn.py:102-116): lane 0 of the
-            // pair turns the L*P logits into softmax weights (and stores them for the backward), lane 1 turns the offsets into
-            // locations ref + offset / (W_l, H_l) -- fp32 division and addition, as the reference's elementwise kernels do.
+            // Module prologue in place on the staged row of (query, head) (ops/modules/ms_deform_attn.py:102-116).  The two lanes of
+            // the pair run ONE instruction stream on the two halves of the row (no divergence): half of the L*P logits each for the
+            // softmax (max and sum exchanged with one shuffle each; ex2-based exp, one reciprocal), half of the samples each for
+            // location = reference point + offset * (1/W_l, 1/H_l) (one FMA).  Against the reference's expf / division kernels that
+            // is a difference of a few ulp in the weights and <= 1 ulp in the locations.
             float *row = reinterpret_cast<float *>(const_cast<TM *>(meta)) + ql * 3 * LP;
-            if (live && part == 0) {
-                float *lg = row + 2 * LP;
-                float mx = lg[0];
-                for (int i = 1; i < LP; ++i) mx = fmaxf(mx, lg[i]);
-                float sum = 0.f;
-                for (int i = 0; i < LP; ++i) {
-                    const float e = expf(lg[i] - mx);
-                    lg[i] = e;
-                    sum += e;
+            const int hl = LP >> 1;                      // LP % 4 == 0 (STAGE)
+            float *lg = row + 2 * LP + part * hl;
+            const float *rf = reinterpret_cast<const float *>(refs0 + ((u - u_lo) & 1) * ref_stride) + ql * sp.L * 2;
+            if (LP == 12 && P == 4) {
+                // the production shape (3 levels x 4 points): the lane's half row lives in registers, vector loads / stores only
+                float2 g0 = make_float2(0.f, 0.f), g1 = g0, g2 = g0;
+                float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0;
+                float4 *xy4 = reinterpret_cast<float4 *>(row) + part * 3;
+                if (live) {
+                    g0 = reinterpret_cast<const float2 *>(lg)[0]; g1 = reinterpret_cast<const float2 *>(lg)[1]; g2 = reinterpret_cast<const float2 *>(lg)[2];
+                    o0 = xy4[0]; o1 = xy4[1]; o2 = xy4[2];
                 }
-                for (int i = 0; i < LP; ++i) lg[i] = __fdiv_rn(lg[i], sum);
-                float4 *ao = reinterpret_cast<float4 *>(reinterpret_cast<float *>(attn_out) + qm * LP);  // LP % 4 == 0 (STAGE)
-                for (int i = 0; i < LP / 4; ++i) ao[i] = reinterpret_cast<const float4 *>(lg)[i];
-            }
-            if (live && part == SPLIT - 1) {
-                const float *rf = reinterpret_cast<const float *>(refs0 + ((u - u_lo) & 1) * ref_stride) + ql * sp.L * 2;
-                for (int l = 0; l < sp.L; ++l) {
-                    const float Wf = (float)sp.W[l], Hf = (float)sp.H[l], rx = rf[2 * l], ry = rf[2 * l + 1];
-                    for (int p = 0; p < P; ++p) {
-                        float *xy = row + 2 * (l * P + p);
-                        xy[0] = __fadd_rn(rx, __fdiv_rn(xy[0], Wf));
-                        xy[1] = __fadd_rn(ry, __fdiv_rn(xy[1], Hf));
+                float mx = fmaxf(fmaxf(fmaxf(g0.x, g0.y), fmaxf(g1.x, g1.y)), fmaxf(g2.x, g2.y));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                g0.x = __expf(g0.x - mx); g0.y = __expf(g0.y - mx); g1.x = __expf(g1.x - mx);
+                g1.y = __expf(g1.y - mx); g2.x = __expf(g2.x - mx); g2.y = __expf(g2.y - mx);
+                float sum = (g0.x + g0.y) + (g1.x + g1.y) + (g2.x + g2.y);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                if (live) {
+                    const float inv = __frcp_rn(sum);
+                    g0.x *= inv; g0.y *= inv; g1.x *= inv; g1.y *= inv; g2.x *= inv; g2.y *= inv;
+                    reinterpret_cast<float2 *>(lg)[0] = g0; reinterpret_cast<float2 *>(lg)[1] = g1; reinterpret_cast<float2 *>(lg)[2] = g2;
+                    float2 *ao = reinterpret_cast<float2 *>(reinterpret_cast<float *>(attn_out) + qm * LP + part * hl);
+                    ao[0] = g0; ao[1] = g1; ao[2] = g2;
+                    // samples part*6 .. part*6+5: part 0 -> levels 0,0,0,0,1,1; part 1 -> levels 1,1,2,2,2,2
+                    const int la = part, lb = part + 1;
+                    const float wa = sp.rw[la], ha = sp.rh[la], wb = sp.rw[lb], hb = sp.rh[lb];
+                    const float xa = rf[2 * la], ya = rf[2 * la + 1], xb = rf[2 * lb], yb = rf[2 * lb + 1];
+                    const bool p0 = part == 0;  // the middle float4 (samples 2, 3 of the half) belongs to level a for part 0, b for part 1
+                    o0.x = __fmaf_rn(o0.x, wa, xa); o0.y = __fmaf_rn(o0.y, ha, ya); o0.z = __fmaf_rn(o0.z, wa, xa); o0.w = __fmaf_rn(o0.w, ha, ya);
+                    o1.x = __fmaf_rn(o1.x, p0 ? wa : wb, p0 ? xa : xb); o1.y = __fmaf_rn(o1.y, p0 ? ha : hb, p0 ? ya : yb);
+                    o1.z = __fmaf_rn(o1.z, p0 ? wa : wb, p0 ? xa : xb); o1.w = __fmaf_rn(o1.w, p0 ? ha : hb, p0 ? ya : yb);
+                    o2.x = __fmaf_rn(o2.x, wb, xb); o2.y = __fmaf_rn(o2.y, hb, yb); o2.z = __fmaf_rn(o2.z, wb, xb); o2.w = __fmaf_rn(o2.w, hb, yb);
+                    xy4[0] = o0; xy4[1] = o1; xy4[2] = o2;
+                }
+            } else {
+                float mx = -3.0e38f;
+                if (live)
+                    for (int i = 0; i < hl; ++i) mx = fmaxf(mx, lg[i]);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                float sum = 0.f;
+                if (live)
+                    for (int i = 0; i < hl; ++i) {
+                        const float e = __expf(lg[i] - mx);
+                        lg[i] = e;
+                        sum += e;
+                    }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                if (live) {
+                    const float inv = __frcp_rn(sum);
+                    float2 *ao = reinterpret_cast<float2 *>(reinterpret_cast<float *>(attn_out) + qm * LP + part * hl);
+                    for (int i = 0; i < hl; i += 2) {
+                        const float2 a2 = make_float2(lg[i] * inv, lg[i + 1] * inv);
+                        *reinterpret_cast<float2 *>(lg + i) = a2;
+                        ao[i >> 1] = a2;
+                    }
+                    float2 *xy = reinterpret_cast<float2 *>(row) + part * hl;
+                    for (int i = 0; i < hl; ++i) {
+                        const int l = (part * hl + i) / P;
+                        float2 v = xy[i];
+                        v.x = __fmaf_rn(v.x, sp.rw[l], rf[2 * l]);
+                        v.y = __fmaf_rn(v.y, sp.rh[l], rf[2 * l + 1]);
+                        xy[i] = v;
                     }
                 }
             }
@@ -442,6 +486,8 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
         sp.prow0[l] = rows;
         sp.hmax[l] = nextafterf((float)sp.H[l], 0.f);
         sp.wmax[l] = nextafterf((float)sp.W[l], 0.f);
+        sp.rw[l] = 1.0f / (float)sp.W[l];
+        sp.rh[l] = 1.0f / (float)sp.H[l];
         sp.wrecip[l] = (unsigned)((0x100000000ULL + sp.W[l] - 1) / sp.W[l]);
         if ((long long)sp.H[l] * sp.W[l] >= 65536) return false;
         rows += (sp.H[l] + 2) * (sp.W[l] + 2);

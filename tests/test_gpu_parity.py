@@ -433,7 +433,7 @@ def test_fused_prologue_function_matches_oracle(pkg, N, spread):
     loc_t = (_dev(ref)[:, :, None, :, None, :] + _dev(off) / norm).contiguous()
     attn_t = torch.softmax(_dev(logits), -1).view(N, Lq, M, L, P).contiguous()
     out2 = pkg.ms_deform_attn_forward(_dev(d["value"]), _dev(d["shapes"]), _dev(d["start"]), loc_t, attn_t, 128)
-    assert rel_err(out.detach().cpu().numpy(), out2.cpu().numpy()) < 2e-6
+    assert rel_err(out.detach().cpu().numpy(), out2.cpu().numpy()) < 5e-6
 
 
 def test_fused_prologue_padding_mask(pkg):

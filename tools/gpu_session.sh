@@ -23,4 +23,14 @@ echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/ncu_launches_bench.log 2>&1
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'slab32|sorted32' -s 4 -c 2 -o $OUT/prof_main python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_full.log 2>&1
+echo "== ncu full, fused prologue kernels"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'slab32|sorted32|softmax_backward|zero_masked' -s 40 -c 4 -o $OUT/prof_fused python tools/module_bench.py 40 > $OUT/ncu_fused.log 2>&1
+# gpurun brings back at most 64 MiB: summarise the reports here and keep only the text
+for r in prof_main prof_fused; do
+  if [ -f $OUT/$r.ncu-rep ]; then
+    python tools/ncu_summary.py $OUT/$r.ncu-rep > $OUT/${r}_summary.txt 2>&1
+    ncu -i $OUT/$r.ncu-rep --page source --csv > $OUT/${r}_source.csv 2>/dev/null
+    rm -f $OUT/$r.ncu-rep
+  fi
+done
 ls -la $OUT
