@@ -102,15 +102,28 @@ __device__ __forceinline__ void load_slab(float4 *slab, const bf16 *__restrict__
         const int W = sp.W[l], cnt = sp.H[l] * W * 4;
         const bf16 *lsrc = src + (long long)sp.start[l] * pixf;
         float4 *ldst = slab + (size_t)(sp.prow0[l] + (W + 2) + 1) * 8;
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const int pix = i >> 2, c = i & 3;
-            const int y = (int)__umulhi((unsigned)pix, sp.wrecip[l]), x = pix - y * W;
-            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(lsrc + (long long)pix * pixf + c * 8));
-            float4 a, b;
-            bf16x8_to_f32(raw, a, b);
-            float4 *d = ldst + (size_t)(y * (W + 2) + x) * 8 + c * 2;
-            d[0] = a;
-            d[1] = b;
+        // four independent 16-byte loads in flight per thread before the first conversion / store (the plain loop serialises
+        // one L2 round trip per iteration: the shared-memory stores may alias the loads as far as the compiler knows)
+        for (int i0 = threadIdx.x; i0 < cnt; i0 += 4 * blockDim.x) {
+            uint4 raw[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = i0 + r * blockDim.x;
+                if (i < cnt) raw[r] = __ldg(reinterpret_cast<const uint4 *>(lsrc + (long long)(i >> 2) * pixf + (i & 3) * 8));
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = i0 + r * blockDim.x;
+                if (i < cnt) {
+                    const int pix = i >> 2, c = i & 3;
+                    const int y = (int)__umulhi((unsigned)pix, sp.wrecip[l]), x = pix - y * W;
+                    float4 a, b;
+                    bf16x8_to_f32(raw[r], a, b);
+                    float4 *d = ldst + (size_t)(y * (W + 2) + x) * 8 + c * 2;
+                    d[0] = a;
+                    d[1] = b;
+                }
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");  // (empty group: keeps the group arithmetic identical to the fp32 path)
     }
