@@ -88,3 +88,29 @@ def test_product_never_imports_oracle():
                     text = open(os.path.join(dirpath, f)).read()
                     assert "oracle" not in text.lower(), "%s mentions the oracle" % os.path.join(dirpath, f)
                     assert "grid_sample" not in text, "%s holds a PyTorch fallback" % f
+
+
+def test_fused_and_host_entry_points_validate_without_a_gpu(lib):
+    """Argument errors of the newer entry points are reported before anything touches the device."""
+    L = lib.load()
+    null = None
+    # fused forward / backward: the reference's batch rule and dtype checks come first (status < 0), as for msda_forward
+    rc = L.msda_fused_forward(0, null, null, null, null, null, null, null, null, null, 160, 4, 1, 32, 1, 1, 4, 128, null, null, 0, null)
+    assert rc == -6 and b"must divide" in L.msda_last_error()
+    rc = L.msda_fused_forward(7, null, null, null, null, null, null, null, null, null, 1, 4, 1, 32, 1, 1, 4, 128, null, null, 0, null)
+    assert rc == -3
+    rc = L.msda_fused_backward(0, null, null, null, null, null, null, null, null, null, null, null, 3, 4, 1, 32, 1, 1, 4, 2, null, null, 0, null)
+    assert rc == -6
+    # shapes the fused path does not take are a plain "no" (no host geometry, wrong dtype)
+    assert L.msda_fused_supported(0, 40, 1029, 8, 32, 3, 1029, 4, null, null, 0) == 0
+    assert L.msda_fused_supported(1, 40, 1029, 8, 32, 3, 1029, 4, null, null, 0) == 0
+    # host pipeline: bad construction arguments, NULL handle
+    import ctypes
+    h = ctypes.c_void_p()
+    assert L.msda_host_pipeline_create(ctypes.byref(h), 0, 0, 3) == -2      # chunk_frames < 1
+    assert L.msda_host_pipeline_create(ctypes.byref(h), 0, 4, 9) == -2      # slots out of range
+    assert L.msda_host_pipeline_create(None, 0, 4, 3) == -1
+    assert L.msda_host_pipeline_destroy(None) == 0
+    assert L.msda_forward_backward_host(None, 0, 0, null, null, null, null, null, null, null, null, null, null,
+                                        1, 4, 1, 32, 1, 1, 4, 128, None, None) == -1
+    assert L.msda_host_pipeline_error(None) == b"NULL pipeline"
