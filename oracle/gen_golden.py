@@ -56,9 +56,32 @@ def import_reference_encoder():
     pkg("refmodeling.transformer_decoder", root + "/transformer_decoder")
     pkg("refmodeling.pixel_decoder.ops", root + "/pixel_decoder/ops")
     import_reference()  # registers the extension stub
-    for name, attrs in (("fvcore", {}), ("fvcore.nn", {}), ("fvcore.nn.weight_init", {}),
+    import collections
+
+    class Conv2d(torch.nn.Conv2d):  # detectron2.layers.Conv2d: conv, then the attached norm, then the activation
+        def __init__(self, *args, **kwargs):
+            norm, activation = kwargs.pop("norm", None), kwargs.pop("activation", None)
+            super().__init__(*args, **kwargs)
+            self.norm, self.activation = norm, activation
+
+        def forward(self, x):
+            x = torch.nn.functional.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+            if self.norm is not None:
+                x = self.norm(x)
+            return self.activation(x) if self.activation is not None else x
+
+    def get_norm(norm, channels):  # detectron2.layers.get_norm for the two settings COMBO uses
+        return None if norm in (None, "") else {"GN": lambda c: torch.nn.GroupNorm(32, c)}[norm](channels)
+
+    def c2_xavier_fill(module):  # fvcore.nn.weight_init.c2_xavier_fill
+        torch.nn.init.kaiming_uniform_(module.weight, a=1)
+        if module.bias is not None:
+            torch.nn.init.constant_(module.bias, 0)
+
+    ShapeSpec = collections.namedtuple("ShapeSpec", ["channels", "height", "width", "stride"], defaults=(None, None, None, None))
+    for name, attrs in (("fvcore", {}), ("fvcore.nn", {}), ("fvcore.nn.weight_init", {"c2_xavier_fill": c2_xavier_fill}),
                         ("detectron2", {}), ("detectron2.config", {"configurable": lambda f: f}),
-                        ("detectron2.layers", {"Conv2d": object, "ShapeSpec": object, "get_norm": None}),
+                        ("detectron2.layers", {"Conv2d": Conv2d, "ShapeSpec": ShapeSpec, "get_norm": get_norm}),
                         ("detectron2.modeling", {"SEM_SEG_HEADS_REGISTRY": types.SimpleNamespace(register=lambda: (lambda c: c))})):
         m = types.ModuleType(name)
         m.__dict__.update(attrs)
@@ -231,6 +254,38 @@ def main():
          **{"src%d" % i: x for i, x in enumerate(srcs)}, **{"pos%d" % i: x for i, x in enumerate(poss)},
          **{"grad_src%d" % i: x.grad for i, x in enumerate(srcs_d)},
          **{"sd_" + k.replace(".", "__"): v for k, v in extra.items()})
+    # ---- the pixel decoder (msdeformattn.py:169-368): the reference class, with detectron2's Conv2d / get_norm / c2_xavier_fill
+    # / ShapeSpec stubbed by their documented semantics (import_reference_encoder registers the stubs) -----------------------------
+    Dec = sys.modules["refmodeling.pixel_decoder.msdeformattn"].MSDeformAttnPixelDecoder
+    Spec = sys.modules["detectron2.layers"].ShapeSpec
+    torch.manual_seed(17)
+    in_shape = {"res2": Spec(channels=16, stride=4), "res3": Spec(channels=24, stride=8), "res4": Spec(channels=32, stride=16),
+                "res5": Spec(channels=48, stride=32)}
+    dec = Dec(in_shape, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=32, transformer_enc_layers=2,
+              conv_dim=256, mask_dim=64, norm="GN", transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+    enc_state = {k: v for k, v in enc.float().state_dict().items()}           # the 2-layer encoder of the case above
+    dec.transformer.load_state_dict(enc_state)
+    fa, fb = torch.randn(256, 4) * 0.2, torch.randn(4, 256 * 9) * 0.2        # the 3x3 output conv as a rank-4 product (small fixture)
+    with torch.no_grad():
+        dec.layer_1.weight.copy_((fa @ fb).view(256, 256, 3, 3))
+        for gn in [m for m in dec.modules() if isinstance(m, torch.nn.GroupNorm)]:
+            gn.weight.normal_(1, 0.1); gn.bias.normal_(0, 0.1)
+    small = {k: v.detach().clone() for k, v in dec.state_dict().items() if not k.startswith("transformer.") and k != "layer_1.weight"}
+    feats = {"res2": torch.randn(1, 16, 20, 24), "res3": torch.randn(1, 24, 10, 12), "res4": torch.randn(1, 32, 5, 6), "res5": torch.randn(1, 48, 3, 3)}
+    dec = dec.double()
+    fd = {k: v.double().requires_grad_(True) for k, v in feats.items()}
+    class KeepDouble:  # forward_features calls .float() on every input (msdeformattn.py:321,346); keep the oracle run in float64
+        def __init__(self, t):
+            self.t = t
+
+        def float(self):
+            return self.t
+    mask_feat, low, multi = dec.forward_features({k: KeepDouble(v) for k, v in fd.items()})
+    wm = torch.randn(mask_feat.shape)
+    ((mask_feat * wm.double()).sum() + low.sum() + sum(m.square().sum() for m in multi)).backward()
+    save("pixel_decoder_d256", mask_features=mask_feat.detach(), low=low.detach(), wm=wm, layer1_fa=fa, layer1_fb=fb,
+         **{"multi%d" % i: m.detach() for i, m in enumerate(multi)}, **{"feat_" + k: v for k, v in feats.items()},
+         **{"grad_" + k: v.grad for k, v in fd.items()}, **{"sd_" + k.replace(".", "__"): v for k, v in small.items()})
     fresh = MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4)
     save("module_init_256", offsets_bias=fresh.sampling_offsets.bias.detach(),
          offsets_weight_absmax=fresh.sampling_offsets.weight.detach().abs().max(),

@@ -543,3 +543,30 @@ def test_encoder_matches_reference_encoder(pkg):
         got.update({"grad_src%d" % i: srcs[i].grad for i in range(3)})
         for k, t in got.items():
             assert rel_err(t.cpu().numpy(), g[k]) < 1e-3, (fused, k, rel_err(t.cpu().numpy(), g[k]))
+
+
+def test_pixel_decoder_matches_reference_decoder(pkg):
+    """MSDeformAttnPixelDecoder.forward_features against the reference class run in float64 (tests/golden/pixel_decoder_d256.npz;
+    detectron2's Conv2d / get_norm / c2_xavier_fill stubbed by their semantics in oracle/gen_golden.py): outputs and input gradients."""
+    from test_host_logic import _pixel_decoder
+    g, ge, gm = load_golden("pixel_decoder_d256"), load_golden("encoder_d256"), load_golden("module_d256")
+    f32 = lambda v: torch.from_numpy(np.asarray(v, dtype=np.float32))
+    sd = {k[3:].replace("__", "."): f32(v) for k, v in g.items() if k.startswith("sd_")}
+    sd["layer_1.weight"] = (f32(g["layer1_fa"]) @ f32(g["layer1_fb"])).view(256, 256, 3, 3)
+    sd.update({"transformer." + k[3:].replace("__", "."): f32(v) for k, v in ge.items() if k.startswith("sd_")})
+    for i in range(2):
+        sd.update({"transformer.encoder.layers.%d.self_attn.%s" % (i, k[3:].replace("__", ".")): f32(v) for k, v in gm.items() if k.startswith("sd_")})
+    dec = _pixel_decoder(pkg)
+    dec.load_state_dict(sd)
+    dec = dec.cuda()
+    feats = {k[5:]: _dev(v, torch.float32).requires_grad_(True) for k, v in g.items() if k.startswith("feat_")}
+    mask_feat, low, multi = dec.forward_features(feats)
+    assert pkg.last_variant("forward") == "slab32+prologue"
+    ((mask_feat * _dev(g["wm"], torch.float32)).sum() + low.sum() + sum(m.square().sum() for m in multi)).backward()
+    torch.cuda.synchronize()
+    assert rel_err(mask_feat.detach().cpu().numpy(), g["mask_features"]) < 1e-4
+    assert rel_err(low.detach().cpu().numpy(), g["low"]) < 1e-4
+    for i, m in enumerate(multi):
+        assert rel_err(m.detach().cpu().numpy(), g["multi%d" % i]) < 1e-4
+    for k, t in feats.items():
+        assert rel_err(t.grad.cpu().numpy(), g["grad_" + k]) < 1e-3, (k, rel_err(t.grad.cpu().numpy(), g["grad_" + k]))

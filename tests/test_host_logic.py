@@ -122,3 +122,30 @@ def test_encoder_classes_mirror_reference_state_dict_and_reference_points(pkg):
     assert torch.equal(ref[:, :, 0], ref[:, :, 1])
     t = MSDeformAttnTransformerEncoder.get_reference_points(torch.tensor(shapes), torch.ones(2, 2, 2), "cpu")
     assert torch.equal(t, ref)
+
+
+def _pixel_decoder(pkg_):
+    from combo_avs_b200.pixel_decoder import MSDeformAttnPixelDecoder
+    shape = {"res2": (16, 4), "res3": (24, 8), "res4": (32, 16), "res5": (48, 32)}
+    return MSDeformAttnPixelDecoder(shape, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=32,
+                                    transformer_enc_layers=2, conv_dim=256, mask_dim=64, norm="GN",
+                                    transformer_in_features=["res3", "res4", "res5"], common_stride=4)
+
+
+def test_pixel_decoder_mirrors_reference_names_and_position_encoding(pkg):
+    """State-dict names equal the reference decoder's (golden written by the reference class); the sine position encoding
+    equals the closed form of position_encoding.py:33-52 for an unpadded map."""
+    from combo_avs_b200.pixel_decoder import PositionEmbeddingSine
+    g, ge, gm = load_golden("pixel_decoder_d256"), load_golden("encoder_d256"), load_golden("module_d256")
+    dec = _pixel_decoder(pkg)
+    want = {k[3:].replace("__", ".") for k in g if k.startswith("sd_")} | {"layer_1.weight"}
+    want |= {"transformer." + k[3:].replace("__", ".") for k in ge if k.startswith("sd_")}
+    want |= {"transformer.encoder.layers.%d.self_attn.%s" % (i, k[3:].replace("__", ".")) for i in range(2) for k in gm if k.startswith("sd_")}
+    assert set(dec.state_dict().keys()) == want
+    assert dec.num_fpn_levels == 1 and dec.in_features == ["res2", "res3", "res4", "res5"]
+    pe = PositionEmbeddingSine(4, normalize=True)(torch.zeros(1, 3, 2, 3))
+    assert pe.shape == (1, 8, 2, 3)
+    import math
+    y = 2 * math.pi * 1 / (2 + 1e-6)                      # first row, normalised
+    assert abs(float(pe[0, 0, 0, 0]) - math.sin(y)) < 1e-6 and abs(float(pe[0, 1, 0, 0]) - math.cos(y)) < 1e-6
+    assert abs(float(pe[0, 2, 0, 0]) - math.sin(y / 10000 ** 0.5)) < 1e-6

@@ -6,6 +6,9 @@ forces float anyway, msdeformattn.py:321).  Arms, same PyTorch code around the o
     fused      -- this package, module prologue + mask inside the kernels (default)
     unfused    -- this package, softmax / locations / masked_fill in PyTorch
     reference  -- the reference's own CUDA extension (oracle/_ref, built by oracle/build_ref.py) behind the same module
+With a third argument "decoder" the whole pixel decoder (msdeformattn.py:169-368: input projections + GroupNorm, position
+encoding, the encoder, the FPN top-down pass and the mask-feature head; COMBO-R50 S4 settings) runs on ResNet-50-shaped synthetic
+backbone features of a 224x224 frame (res2 256x56x56 ... res5 2048x7x7) instead of the bare encoder.
 Under torchrun (WORLD_SIZE > 1) the encoder is wrapped in DistributedDataParallel: one process per GPU, every rank its own
 frames (weak scaling), NCCL only for the gradient all-reduce.  Prints one JSON object (rank 0)."""
 import json, os, statistics, sys, time
@@ -20,6 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import combo_avs_b200 as pkg
 from combo_avs_b200 import modules as pkg_modules
 from combo_avs_b200.encoder import MSDeformAttnTransformerEncoderOnly
+from combo_avs_b200.pixel_decoder import MSDeformAttnPixelDecoder
 
 S4 = [(7, 7), (14, 14), (28, 28)]
 
@@ -45,6 +49,7 @@ class _RefFunction(torch.autograd.Function):
 def main():
     frames = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+    decoder = len(sys.argv) > 3 and sys.argv[3] == "decoder"
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -54,7 +59,10 @@ def main():
     srcs = [torch.randn(frames, 256, h, w, generator=g).to(dev) for h, w in S4]
     poss = [torch.randn(frames, 256, h, w, generator=g).to(dev) * 0.5 for h, w in S4]
     gmem = torch.randn(frames, sum(h * w for h, w in S4), 256, generator=g).to(dev)
-    res = {"frames_per_gpu": frames, "n_gpus": world, "layers": 6, "dtype": "f32", "arms": {}}
+    r50 = {"res2": (256, 4), "res3": (512, 8), "res4": (1024, 16), "res5": (2048, 32)}
+    feats = {k: torch.randn(frames, c, 224 // s, 224 // s, generator=g).to(dev) for k, (c, s) in r50.items()} if decoder else None
+    res = {"workload": "pixel decoder (R50-shaped features, 224x224)" if decoder else "deformable encoder", "frames_per_gpu": frames,
+           "n_gpus": world, "layers": 6, "dtype": "f32", "arms": {}}
     import build_ref
     ref_ext = build_ref.load_ref()
     arms = [("fused", True, None), ("unfused", False, None)] + ([("reference", False, ref_ext)] if ref_ext is not None else [])
@@ -62,8 +70,14 @@ def main():
     original = pkg_modules.MSDeformAttnFunction
     for name, fuse, ext in arms:
         torch.manual_seed(7)
-        enc = MSDeformAttnTransformerEncoderOnly(d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.0,
-                                                 num_feature_levels=3, enc_n_points=4).to(dev)
+        if decoder:
+            top = MSDeformAttnPixelDecoder(r50, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
+                                           transformer_enc_layers=6, conv_dim=256, mask_dim=256, norm="GN",
+                                           transformer_in_features=["res3", "res4", "res5"], common_stride=4).to(dev)
+            enc = top.transformer
+        else:
+            top = enc = MSDeformAttnTransformerEncoderOnly(d_model=256, nhead=8, num_encoder_layers=6, dim_feedforward=1024, dropout=0.0,
+                                                           num_feature_levels=3, enc_n_points=4).to(dev)
         with torch.no_grad():  # off the zero init, so offsets / weights vary per query as in a trained model
             for layer in enc.encoder.layers:
                 layer.self_attn.sampling_offsets.weight.normal_(0, 0.02)
@@ -72,16 +86,23 @@ def main():
         torch.backends.cuda.matmul.allow_tf32 = name.endswith("tf32_matmul")
         _RefFunction.ext = ext
         pkg_modules.MSDeformAttnFunction = _RefFunction if ext is not None else original
-        model = torch.nn.parallel.DistributedDataParallel(enc, device_ids=[local]) if world > 1 else enc
+        model = torch.nn.parallel.DistributedDataParallel(top, device_ids=[local]) if world > 1 else top
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
         inputs = [x.clone().requires_grad_(True) for x in srcs]
+        fin = {k: v.clone().requires_grad_(True) for k, v in feats.items()} if decoder else None
 
         def step():
             opt.zero_grad(set_to_none=True)
-            for x in inputs:
-                x.grad = None
-            memory, _, _ = model(inputs, poss)
-            memory.backward(gmem)
+            if decoder:
+                for x in fin.values():
+                    x.grad = None
+                mask_feat, low, multi = model(fin)
+                (mask_feat.mean() + low.mean() + sum(m.mean() for m in multi)).backward()
+            else:
+                for x in inputs:
+                    x.grad = None
+                memory, _, _ = model(inputs, poss)
+                memory.backward(gmem)
             opt.step()
 
         for _ in range(5):
@@ -100,7 +121,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         res["arms"][name] = {"ms_per_step": ms, "frames_per_s": world * frames / (ms * 1e-3), "msda_launches_per_step": (pkg.launch_count() - l0) / iters}
-        del model, enc, opt
+        del model, enc, top, opt
     pkg_modules.MSDeformAttnFunction = original
     torch.backends.cuda.matmul.allow_tf32 = False
     if "reference" in res["arms"]:
