@@ -560,10 +560,15 @@ def test_pixel_decoder_matches_reference_decoder(pkg):
     dec.load_state_dict(sd)
     dec = dec.cuda()
     feats = {k[5:]: _dev(v, torch.float32).requires_grad_(True) for k, v in g.items() if k.startswith("feat_")}
-    mask_feat, low, multi = dec.forward_features(feats)
-    assert pkg.last_variant("forward") == "slab32+prologue"
-    ((mask_feat * _dev(g["wm"], torch.float32)).sum() + low.sum() + sum(m.square().sum() for m in multi)).backward()
-    torch.cuda.synchronize()
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # PyTorch's default lets cuDNN run the convolutions in TF32 (5e-4 against float64)
+    try:
+        mask_feat, low, multi = dec.forward_features(feats)
+        assert pkg.last_variant("forward") == "slab32+prologue"
+        ((mask_feat * _dev(g["wm"], torch.float32)).sum() + low.sum() + sum(m.square().sum() for m in multi)).backward()
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
     assert rel_err(mask_feat.detach().cpu().numpy(), g["mask_features"]) < 1e-4
     assert rel_err(low.detach().cpu().numpy(), g["low"]) < 1e-4
     for i, m in enumerate(multi):
