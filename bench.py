@@ -326,6 +326,15 @@ def run_ours(args):
         cpu = {"value": sample / sec, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d frames x %d fwd+bwd steps, fp32, torch %s CPU path restating ms_deform_attn_core_pytorch (oracle/core_pytorch.py)" % (sample, iters, torch.__version__),
                "ms_per_step": sec * 1e3}
+        # the same path on ONE host thread as well (2-frame sample), and which CPU this is
+        sec1, _ = time_cpu_port(torch, 2, 2, 1, threads=1)
+        cpu["single_thread"] = {"value": 2 / sec1, "unit": UNIT, "cores": 1, "sample": "2 frames x 2 fwd+bwd steps"}
+        torch.set_num_threads(threads)
+        try:
+            with open("/proc/cpuinfo") as f:
+                cpu["cpu_model"] = next((l.split(":", 1)[1].strip() for l in f if l.startswith("model name")), None)
+        except OSError:
+            cpu["cpu_model"] = None
 
     if rank == 0:
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
