@@ -47,11 +47,6 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
 using bf16 = __nv_bfloat16;
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
