@@ -575,3 +575,25 @@ def test_pixel_decoder_matches_reference_decoder(pkg):
         assert rel_err(m.detach().cpu().numpy(), g["multi%d" % i]) < 1e-4
     for k, t in feats.items():
         assert rel_err(t.grad.cpu().numpy(), g["grad_" + k]) < 1e-3, (k, rel_err(t.grad.cpu().numpy(), g["grad_" + k]))
+
+
+# ----------------------------------------------------------------------------------------------- bench.py contract
+def test_bench_prints_one_json_line_with_the_contract_keys():
+    """A short run of bench.py: exactly one line on stdout, the keys the driver reads, sane values."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu", "--frames", "8"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] >= 3 and d["dtype"] == "f32" and d["scaling"] == "weak"
+    assert d["value"] > 0 and d["gpu_launches"] == 2 * 5 and "workload" in d["config"]
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and 0 < rf["frac"] < 1 and abs(rf["achieved"] / rf["peak"] - rf["frac"]) < 1e-9
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
