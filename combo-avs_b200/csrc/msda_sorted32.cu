@@ -151,12 +151,13 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
     const int n_mine = sp.base + ((int)blockIdx.x < sp.rem * sp.parts ? 1 : 0);
     for (int ui = 0; ui < n_mine; ++ui) {
         const bool piece = ui == sp.base;
-        const long long u = piece ? (long long)gridDim.x * sp.base + blockIdx.x / sp.parts : (long long)blockIdx.x * sp.base + ui;
+        // (32-bit unit arithmetic: every thread decodes its unit, and 64-bit divisions are ~100 instructions each)
+        const int u = piece ? (int)gridDim.x * sp.base + (int)blockIdx.x / sp.parts : (int)blockIdx.x * sp.base + ui;
         const int part = piece ? (int)blockIdx.x % sp.parts : 0, parts = piece ? sp.parts : 1;
-        const long long nm = u / sp.L;
-        const int l = (int)(u - nm * sp.L);
+        const int nm = u / sp.L;
+        const int l = u - nm * sp.L;
         const long long n = nm / sp.M;
-        const int m = (int)(nm - n * sp.M);
+        const int m = nm - (int)n * sp.M;
         const int H = sp.H[l], W = sp.W[l], cs = sp.cshift[l], cells = (H + 1) << cs, Wp = W + 2;
         const float Hf = (float)H, Wf = (float)W;
         const long long lvl_row = (n * sp.S + sp.start[l]) * (long long)pix + (long long)m * kD;  // pixel (0,0), channel 0
@@ -309,10 +310,10 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         // ---- L2 prefetch of the next whole unit of this CTA: its locations / weights, its value rows and, when it starts a new
         // (frame, head) slab, its grad_out rows -- so that the next sort and walk find them in L2 instead of paying HBM latency
         if (sp.prefetch && ui + 1 < sp.base) {
-            const long long u2 = u + 1, nm2 = u2 / sp.L;
-            const int l2 = (int)(u2 - nm2 * sp.L);
+            const int u2 = u + 1, nm2 = u2 / sp.L;
+            const int l2 = u2 - nm2 * sp.L;
             const long long n2 = nm2 / sp.M;
-            const int m2 = (int)(nm2 - n2 * sp.M);
+            const int m2 = nm2 - (int)n2 * sp.M;
             const long long meta2 = ((n2 * Lq) * sp.M + m2) * (long long)LP + l2 * P;
             const TM *loc2 = loc + 2 * meta2, *att2 = attn + meta2;
             for (int q = tid; q < Lq; q += kThreads) {
@@ -340,10 +341,10 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         };
         int E0 = 0, E = Etot;
         if (parts > 1) {
-            E0 = part == 0 ? 0 : cell_boundary((int)((long long)Etot * part / parts));
-            E = (part + 1 == parts ? Etot : cell_boundary((int)((long long)Etot * (part + 1) / parts))) - E0;
+            E0 = part == 0 ? 0 : cell_boundary(Etot * part / parts);
+            E = (part + 1 == parts ? Etot : cell_boundary(Etot * (part + 1) / parts)) - E0;
         }
-        const int e_lo = E0 + (int)((long long)E * grp / kGroups), e_hi = E0 + (int)((long long)E * (grp + 1) / kGroups);
+        const int e_lo = E0 + E * grp / kGroups, e_hi = E0 + E * (grp + 1) / kGroups;  // E <= 4608, grp < 384: fits 32 bits
         // grad_out row of query q: gobase + q*pix (+ chf[k]); streamed from L2, prefetched one entry ahead
         const TV *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD;
         float *gbase = grad_value + lvl_row;
@@ -595,6 +596,7 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
         sp.wrecip[l] = (unsigned)((0x100000000ULL + sp.W[l] - 1) / sp.W[l]);
     }
     sp.units = (long long)p.N * p.M * p.L;
+    if (sp.units >= (1LL << 30)) return false;  // 32-bit unit arithmetic in the kernel
     smem = (size_t)sp.vrows_max * 8 * 16 + (size_t)p.Lq * p.P * 16 + (kMaxCells + 8 + 32) * sizeof(int);
     if (smem > (size_t)p.smem_optin) return false;
     // three private 16-byte slots per chunk per thread for the cp.async grad_out pipeline, when they fit
