@@ -126,6 +126,9 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
     int *cell_off = reinterpret_cast<int *>(ent + EP);    // kMaxCells + 1 counters -> exclusive offsets
     int *warp_tot = cell_off + kMaxCells + 8;
     constexpr bool GRING = (MODE & 1) != 0, DEFER = (MODE & 2) != 0, FUSED = (MODE & 4) != 0;
+    // MODE bit 4 (16): fewer FMA-pipe instructions per sample -- four dot products of grad_out with (V00, dW, dH, dd) combined after
+    // the horizontal add, and grad_value accumulated in the basis (1, lw, lh, lh*lw) and converted to the four neighbours at flush
+    constexpr bool LEAN = (MODE & 16) != 0;
     // GRING: slot (stage, k) of thread t at gring + ((stage*CH + k) * kThreads + t) * 16 bytes, three stages
     unsigned gslot_s = (unsigned)__cvta_generic_to_shared(warp_tot + 32) + threadIdx.x * 16;
     pin(gslot_s);
@@ -371,6 +374,11 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 float *gk = gp + chf[k];
+                if (LEAN) {  // (S0, S1, S2, S3) = sums of att * (1, lw, lh, lh*lw) * g  ->  the four bilinear weights
+                    a10[k] = psub(a10[k], a11[k]);                    // lh*(1-lw)
+                    a00[k] = psub(psub(a00[k], a01[k]), a10[k]);      // (1-lh)*(1-lw) = S0 - S1 - (S2 - S3)
+                    a01[k] = psub(a01[k], a11[k]);                    // (1-lh)*lw
+                }
                 if (inmask & 1) red_add_v4(gk, a00[k].lo.x, a00[k].lo.y, a00[k].hi.x, a00[k].hi.y);
                 if (inmask & 2) red_add_v4(gk + o01, a01[k].lo.x, a01[k].lo.y, a01[k].hi.x, a01[k].hi.y);
                 if (inmask & 4) red_add_v4(gk + o10, a10[k].lo.x, a10[k].lo.y, a10[k].hi.x, a10[k].hi.y);
@@ -456,6 +464,27 @@ _Pragma("unroll") \
                     } \
                 } \
                 const float lh = en.x, lw = en.y; \
+                if (LEAN) { \
+                    const float a1s = att_v * lw, a2s = att_v * lh, a3s = a2s * lw; \
+                    const float2 b0 = make_float2(att_v, att_v), b1 = make_float2(a1s, a1s), b2 = make_float2(a2s, a2s), b3 = make_float2(a3s, a3s); \
+                    float2 qA = z2, qB = z2, qC = z2, qE = z2; \
+_Pragma("unroll") \
+                    for (int k = 0; k < CH; ++k) { \
+                        const f4p g = pk(gr[k]); \
+                        qA = __ffma2_rn(g.hi, v00[k].hi, __ffma2_rn(g.lo, v00[k].lo, qA)); \
+                        qB = __ffma2_rn(g.hi, dW[k].hi, __ffma2_rn(g.lo, dW[k].lo, qB)); \
+                        qC = __ffma2_rn(g.hi, dH[k].hi, __ffma2_rn(g.lo, dH[k].lo, qC)); \
+                        qE = __ffma2_rn(g.hi, dd[k].hi, __ffma2_rn(g.lo, dd[k].lo, qE)); \
+                        a00[k].lo = __ffma2_rn(b0, g.lo, a00[k].lo); a00[k].hi = __ffma2_rn(b0, g.hi, a00[k].hi); \
+                        a01[k].lo = __ffma2_rn(b1, g.lo, a01[k].lo); a01[k].hi = __ffma2_rn(b1, g.hi, a01[k].hi); \
+                        a10[k].lo = __ffma2_rn(b2, g.lo, a10[k].lo); a10[k].hi = __ffma2_rn(b2, g.hi, a10[k].hi); \
+                        a11[k].lo = __ffma2_rn(b3, g.lo, a11[k].lo); a11[k].hi = __ffma2_rn(b3, g.hi, a11[k].hi); \
+                    } \
+                    const float A = qA.x + qA.y, B = qB.x + qB.y, C = qC.x + qC.y, E = qE.x + qE.y; \
+                    s_w = __fmaf_rn(lh, E, B); \
+                    s_h = __fmaf_rn(lw, E, C); \
+                    s_a = __fmaf_rn(lh, s_h, __fmaf_rn(lw, B, A)); \
+                } else { \
                 const float ah = (1.f - lh) * att_v, al = lh * att_v, hw = 1.f - lw; \
                 const float2 lh2 = make_float2(lh, lh), lw2 = make_float2(lw, lw); \
                 const float2 w1 = make_float2(ah * hw, ah * hw), w2 = make_float2(ah * lw, ah * lw); \
@@ -478,6 +507,7 @@ _Pragma("unroll") \
                 s_a = pa.x + pa.y; \
                 s_h = ph.x + ph.y; \
                 s_w = pw.x + pw.y; \
+                } \
             } \
             if (SPLIT == 2) { \
                 s_a += __shfl_xor_sync(0xffffffffu, s_a, 1); \
@@ -562,9 +592,9 @@ int sorted_split()
     return v;
 }
 
-int sorted_mode()  // bit 0: cp.async grad_out ring, bit 1: deferred reduction
+int sorted_mode()  // bit 0: cp.async grad_out ring, bit 1: deferred reduction, bit 4 (16, the default): lean per-sample arithmetic
 {
-    static const int v = [] { const char *e = getenv("MSDA_SORTED_MODE"); return e ? atoi(e) & 3 : 0; }();
+    static const int v = [] { const char *e = getenv("MSDA_SORTED_MODE"); return e ? atoi(e) & 19 : 16; }();
     return v;
 }
 bool sorted_prefetch()
@@ -608,7 +638,7 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
     sp.prefetch = sorted_prefetch() ? 1 : 0;
     sp.fused = p.ref != nullptr ? 1 : 0;
     if (sp.fused && p.loc_dtype != 0) return false;
-    if (sp.fused) mode = 0;
+    if (sp.fused) mode &= 16;
     return true;
 }
 
@@ -622,7 +652,8 @@ cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc,
     };
     auto pick_mode = [&](auto pt) {
         using std::integral_constant;
-        if (sp.fused) return pick(pt, integral_constant<int, 4>());  // fused prologue: plain register pipeline
+        if (sp.fused) return (mode & 16) ? pick(pt, integral_constant<int, 20>()) : pick(pt, integral_constant<int, 4>());  // fused prologue
+        if (mode & 16) return (mode & 2) ? pick(pt, integral_constant<int, 18>()) : (mode & 1) ? pick(pt, integral_constant<int, 17>()) : pick(pt, integral_constant<int, 16>());
         return mode == 3 ? pick(pt, integral_constant<int, 3>()) : mode == 2 ? pick(pt, integral_constant<int, 2>())
              : mode == 1 ? pick(pt, integral_constant<int, 1>()) : pick(pt, integral_constant<int, 0>());
     };
