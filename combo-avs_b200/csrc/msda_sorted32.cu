@@ -349,7 +349,9 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         }
         const int e_lo = E0 + E * grp / kGroups, e_hi = E0 + E * (grp + 1) / kGroups;  // E <= 4608, grp < 384: fits 32 bits
         // grad_out row of query q: gobase + q*pix (+ chf[k]); streamed from L2, prefetched one entry ahead
-        const TV *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD;
+        const TV *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD + chf[0];  // (this lane's first chunk folded in)
+        unsigned grow_b = (unsigned)pix * (unsigned)sizeof(TV);  // bytes between the grad_out rows of consecutive queries
+        pin(grow_b);
         float *gbase = grad_value + lvl_row;
         const int o01 = pix, o10 = W * pix, o11 = (W + 1) * pix;
         unsigned V_s = (unsigned)__cvta_generic_to_shared(V4);
@@ -390,18 +392,19 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         auto issue_g = [&](int e2, int si, float4 (&g)[CH]) {
             unsigned packed;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(ent_s + min(e2, e_hi - 1) * 16 + 12));
-            const TV *gq = gobase + (packed & 0xffff) * pixv;
+            // 64-bit base + unsigned 32-bit byte offset: two adds instead of a sign-extended 64-bit multiply-shift chain
+            const TV *gq = reinterpret_cast<const TV *>(reinterpret_cast<const char *>(gobase) + (packed & 0xffff) * grow_b);
             if (GRING) {
 #pragma unroll
                 for (int k = 0; k < CH; ++k) {
                     const unsigned slot = gslot_s + (unsigned)((si * CH + k) * kThreads) * 16;
-                    if (sizeof(TV) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(gq + chf[k]) : "memory");
-                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot), "l"(gq + chf[k]) : "memory");
+                    if (sizeof(TV) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(gq + (chf[k] - chf[0])) : "memory");
+                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot), "l"(gq + (chf[k] - chf[0])) : "memory");
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             } else {
 #pragma unroll
-                for (int k = 0; k < CH; ++k) g[k] = load4(gq + chf[k]);
+                for (int k = 0; k < CH; ++k) g[k] = load4(gq + (chf[k] - chf[0]));
             }
         };
         // GRING: wait for the copy into slot `si` (all but the two newest groups, or everything when `drain`) and read it back
@@ -424,16 +427,18 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
             }
         };
         // deferred tail of the previous sample (DEFER): its three lane-partial sums, weight and result index
-        float d_a = 0.f, d_h = 0.f, d_w = 0.f, d_att = 0.f;
+        float d_a = 0.f, d_h = 0.f, d_w = 0.f;
         int d_idx = -1;
-        auto finish = [&](float s_a, float s_h, float s_w, float att_v, int sidx) {  // SPLIT >= 4: transposed butterfly + stores
+        // s_h / s_w arrive already multiplied by the sample's attention weight (cuh:126-127), so the tail is one multiply per lane
+        auto finish = [&](float s_a, float s_h, float s_w, int sidx) {  // SPLIT >= 4: transposed butterfly + stores
             float x = (j & 1) ? s_h : s_a;
             x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1);
             s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);
             float keep = (j & 2) ? s_w : x;
             keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2);
             if (SPLIT == 8) keep += __shfl_xor_sync(0xffffffffu, keep, 4);
-            if (sidx >= 0 && j < 3) store1(res_base + sidx * res_stride, keep * res_scale * (j == 0 ? 1.f : att_v));
+            if (sidx >= 0 && j < 3)
+                store1(res_base + sidx * res_stride, keep * res_scale);
         };
         // one sample: en = its sorted entry, gr = its grad_out chunks (both already in registers)
 #define MSDA_SAMPLE_BODY \
@@ -518,10 +523,10 @@ _Pragma("unroll") \
                     else store1(res_base + sidx, s_a); \
                 } \
             } else if (DEFER) { \
-                finish(d_a, d_h, d_w, d_att, d_idx); \
-                d_a = s_a; d_h = s_h; d_w = s_w; d_att = att_v; d_idx = active ? sidx : -1; \
+                finish(d_a, d_h, d_w, d_idx); \
+                d_a = s_a; d_h = s_h * att_v; d_w = s_w * att_v; d_idx = active ? sidx : -1; \
             } else { \
-                finish(s_a, s_h, s_w, att_v, active ? sidx : -1); \
+                finish(s_a, s_h * att_v, s_w * att_v, active ? sidx : -1); \
             }
         // nvcc 12.9 crashes on a generic lambda here, hence two plain lambdas sharing one body
         auto sample_steady = [&](const float4 &en, const float4 (&gr)[CH]) {
@@ -577,7 +582,7 @@ _Pragma("unroll") \
             sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g2, e < e_hi);
         }
         if (DEFER && SPLIT >= 4) {
-            finish(d_a, d_h, d_w, d_att, d_idx);
+            finish(d_a, d_h, d_w, d_idx);
             d_idx = -1;
         }
         if (GRING) asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing may land in a slot during the next unit
