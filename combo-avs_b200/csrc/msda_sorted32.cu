@@ -130,7 +130,12 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
     // the horizontal add, and grad_value accumulated in the basis (1, lw, lh, lh*lw) and converted to the four neighbours at flush
     constexpr bool LEAN = (MODE & 16) != 0;
     // GRING: slot (stage, k) of thread t at gring + ((stage*CH + k) * kThreads + t) * 16 bytes, three stages
-    unsigned gslot_s = (unsigned)__cvta_generic_to_shared(warp_tot + 32) + threadIdx.x * 16;
+    // per-cell facts of the current level, filled while the unit is sorted: {value-slab byte offset of the cell's top-left
+    // neighbour | 4-bit mask of the neighbours inside the map, grad_value element offset of that neighbour}
+    int2 *cinfo = reinterpret_cast<int2 *>(warp_tot + 32);
+    unsigned cinfo_s = (unsigned)__cvta_generic_to_shared(cinfo);
+    pin(cinfo_s);
+    unsigned gslot_s = (unsigned)__cvta_generic_to_shared(cinfo + kMaxCells) + threadIdx.x * 16;
     pin(gslot_s);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int grp = tid / SPLIT;
@@ -221,6 +226,12 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
             }
         }
         for (int i = tid; i <= cells; i += kThreads) cell_off[i] = 0;
+        for (int c = tid; c < cells; c += kThreads) {
+            const int cy = c >> cs, cx = c & ((1 << cs) - 1);
+            const int inm = ((cy >= 1 && cx >= 1) ? 1 : 0) | ((cy >= 1 && cx <= W - 1) ? 2 : 0) |
+                            ((cy <= H - 1 && cx >= 1) ? 4 : 0) | ((cy <= H - 1 && cx <= W - 1) ? 8 : 0);
+            cinfo[c] = make_int2((cy * Wp + cx) * (kD * 4) | inm, ((cy - 1) * W + cx - 1) * pix);
+        }
 
         __syncthreads();  // counters are zero
 #pragma unroll
@@ -356,8 +367,8 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         const int o01 = pix, o10 = W * pix, o11 = (W + 1) * pix;
         unsigned V_s = (unsigned)__cvta_generic_to_shared(V4);
         pin(V_s);
-        int qs = qstride, pixv = pix, Wv = W, Wpb = Wp * (kD * 4);
-        pin(qs); pin(pixv); pin(Wv); pin(Wpb);
+        int qs = qstride, Wpb = Wp * (kD * 4);
+        pin(qs); pin(Wpb);
         // result stores: SPLIT >= 4: lane 0 grad_attn, lane 1 grad_loc.y, lane 2 grad_loc.x; SPLIT == 2: lane 0 grad_loc (float2), lane 1 grad_attn
         TM *res_base = SPLIT >= 4 ? (j == 0 ? gatt : gloc + (j == 1 ? 1 : 0)) : (j == 0 ? gloc : gatt);
         int res_stride = SPLIT >= 4 ? (j == 0 ? 1 : 2) : (j == 0 ? 2 : 1);
@@ -452,11 +463,11 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                 if (cell != cur) { \
                     flush(); \
                     cur = cell; \
-                    const int cy = cell >> cs, cx = cell & ((1 << cs) - 1); \
-                    inmask = ((cy >= 1 && cx >= 1) ? 1 : 0) | ((cy >= 1 && cx <= Wv - 1) ? 2 : 0) | \
-                             ((cy <= H - 1 && cx >= 1) ? 4 : 0) | ((cy <= H - 1 && cx <= Wv - 1) ? 8 : 0); \
-                    gp = gbase + ((cy - 1) * Wv + cx - 1) * pixv; \
-                    const unsigned vr = V_s + (unsigned)(cy * Wpb + cx * (kD * 4)); \
+                    int2 ci; \
+                    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(ci.x), "=r"(ci.y) : "r"(cinfo_s + cell * 8)); \
+                    inmask = ci.x & 15; \
+                    gp = gbase + ci.y; \
+                    const unsigned vr = V_s + (unsigned)(ci.x & ~127); \
 _Pragma("unroll") \
                     for (int k = 0; k < CH; ++k) { \
                         const unsigned a = vr + chf[k] * 4; \
@@ -632,7 +643,7 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
     }
     sp.units = (long long)p.N * p.M * p.L;
     if (sp.units >= (1LL << 30)) return false;  // 32-bit unit arithmetic in the kernel
-    smem = (size_t)sp.vrows_max * 8 * 16 + (size_t)p.Lq * p.P * 16 + (kMaxCells + 8 + 32) * sizeof(int);
+    smem = (size_t)sp.vrows_max * 8 * 16 + (size_t)p.Lq * p.P * 16 + (kMaxCells + 8 + 32) * sizeof(int) + kMaxCells * sizeof(int2);
     if (smem > (size_t)p.smem_optin) return false;
     // three private 16-byte slots per chunk per thread for the cp.async grad_out pipeline, when they fit
     const int split = sorted_split();
