@@ -69,6 +69,13 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// the same, predicated inside the instruction: no branch / reconvergence around it when only some lanes reduce
+__device__ __forceinline__ void red_add_v4_if(int pred, float *p, float a, float b, float c, float d)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "r"(pred) : "memory");
+}
+
 __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
 __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
 

@@ -387,15 +387,17 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 float *gk = gp + chf[k];
-                if (LEAN) {  // (S0, S1, S2, S3) = sums of att * (1, lw, lh, lh*lw) * g  ->  the four bilinear weights
-                    a10[k] = psub(a10[k], a11[k]);                    // lh*(1-lw)
-                    a00[k] = psub(psub(a00[k], a01[k]), a10[k]);      // (1-lh)*(1-lw) = S0 - S1 - (S2 - S3)
-                    a01[k] = psub(a01[k], a11[k]);                    // (1-lh)*lw
+                f4p r00 = a00[k], r01 = a01[k], r10 = a10[k];
+                if (LEAN) {  // (S0, S1, S2, S3) = sums of att * (1, lw, lh, lh*lw) * g  ->  the four bilinear weights (into temporaries:
+                             // the accumulators themselves are only ever zeroed, so no register moves at the branch merge)
+                    r10 = psub(a10[k], a11[k]);                    // lh*(1-lw)
+                    r00 = psub(psub(a00[k], a01[k]), r10);         // (1-lh)*(1-lw) = S0 - S1 - (S2 - S3)
+                    r01 = psub(a01[k], a11[k]);                    // (1-lh)*lw
                 }
-                if (inmask & 1) red_add_v4(gk, a00[k].lo.x, a00[k].lo.y, a00[k].hi.x, a00[k].hi.y);
-                if (inmask & 2) red_add_v4(gk + o01, a01[k].lo.x, a01[k].lo.y, a01[k].hi.x, a01[k].hi.y);
-                if (inmask & 4) red_add_v4(gk + o10, a10[k].lo.x, a10[k].lo.y, a10[k].hi.x, a10[k].hi.y);
-                if (inmask & 8) red_add_v4(gk + o11, a11[k].lo.x, a11[k].lo.y, a11[k].hi.x, a11[k].hi.y);
+                red_add_v4_if(inmask & 1, gk, r00.lo.x, r00.lo.y, r00.hi.x, r00.hi.y);
+                red_add_v4_if(inmask & 2, gk + o01, r01.lo.x, r01.lo.y, r01.hi.x, r01.hi.y);
+                red_add_v4_if(inmask & 4, gk + o10, r10.lo.x, r10.lo.y, r10.hi.x, r10.hi.y);
+                red_add_v4_if(inmask & 8, gk + o11, a11[k].lo.x, a11[k].lo.y, a11[k].hi.x, a11[k].hi.y);
             }
         };
         // start the loads of the grad_out chunks of sorted entry e2 (clamped to this group's range): into the lane's shared-memory
