@@ -67,10 +67,10 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4 &r, float4 &a, float4 
 }
 
 // copy value[n, :, m, :] into the padded fp32 slab (interior only; the border was zeroed once)
-__device__ __forceinline__ void load_slab(float4 *slab, const float *__restrict__ value, const SlabParams &sp, long long nm)
+__device__ __forceinline__ void load_slab(float4 *slab, const float *__restrict__ value, const SlabParams &sp, int nm)
 {
-    const long long n = nm / sp.M;
-    const int m = (int)(nm - n * sp.M);
+    const long long n = nm / sp.M;  // (32-bit division; 64-bit only for the element offsets below)
+    const int m = nm - (int)n * sp.M;
     const float *src = value + ((n * sp.S) * sp.M + m) * kD;
     const int pixf = sp.M * kD;
     for (int l = 0; l < sp.L; ++l) {
@@ -87,10 +87,10 @@ __device__ __forceinline__ void load_slab(float4 *slab, const float *__restrict_
 }
 
 // bf16 values: rows are 64 bytes in HBM; they are widened to fp32 on the way into the slab (the gather itself is unchanged)
-__device__ __forceinline__ void load_slab(float4 *slab, const bf16 *__restrict__ value, const SlabParams &sp, long long nm)
+__device__ __forceinline__ void load_slab(float4 *slab, const bf16 *__restrict__ value, const SlabParams &sp, int nm)
 {
     const long long n = nm / sp.M;
-    const int m = (int)(nm - n * sp.M);
+    const int m = nm - (int)n * sp.M;
     const bf16 *src = value + ((n * sp.S) * sp.M + m) * kD;
     const int pixf = sp.M * kD;
     for (int l = 0; l < sp.L; ++l) {
@@ -167,11 +167,11 @@ __device__ __forceinline__ void floor_split(float x, float &fl, int &i)
 // pieces issued by consecutive lanes touch each 128-byte line once, instead of once per sample per query.
 template <typename TM>
 __device__ __forceinline__ void stage_meta(TM *meta, const TM *__restrict__ loc, const TM *__restrict__ attn,
-                                           const SlabParams &sp, int LP, long long nm, int q0, int cnt,
+                                           const SlabParams &sp, int LP, int nm, int q0, int cnt,
                                            TM *refs, const TM *__restrict__ ref, int rows_per_warp)
 {
     const long long n = nm / sp.M;
-    const int m = (int)(nm - n * sp.M);
+    const int m = nm - (int)n * sp.M;
     const int pieces = (3 * LP) >> 2, loc_pieces = LP >> 1;  // pieces of 4 elements (16 bytes of fp32, 8 bytes of bf16)
     // rows_per_warp > 0: every warp stages only the rows its own lanes will read (no CTA barrier needed per pass);
     // rows_per_warp == 0: the whole CTA stages the whole pass
@@ -247,7 +247,9 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
             lv[(y * Wp + side * (Wp - 1)) * 8 + c] = z;
         }
     }
-    const long long u_lo = sp.units * blockIdx.x / gridDim.x, u_hi = sp.units * (blockIdx.x + 1) / gridDim.x;
+    // (unit and slab indices fit 32 bits -- checked on the host; every thread decodes them every pass, and 64-bit divisions cost
+    // ~100 instructions each)
+    const int u_lo = (int)(sp.units * blockIdx.x / gridDim.x), u_hi = (int)(sp.units * (blockIdx.x + 1) / gridDim.x);
     int ql = threadIdx.x / SPLIT;
     const int part = threadIdx.x % SPLIT;
     pin(ql);
@@ -261,20 +263,20 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
     }
     unsigned slab_s = (unsigned)__cvta_generic_to_shared(slab);
     pin(slab_s);
-    long long resident = -1;
-    auto pass_range = [&](long long u, long long &nm, int &q0, int &cnt) {
+    int resident = -1;
+    auto pass_range = [&](int u, int &nm, int &q0, int &cnt) {
         nm = u / sp.pps;
-        q0 = (int)(u - nm * sp.pps) * sp.qpp;
+        q0 = (u - nm * sp.pps) * sp.qpp;
         cnt = min(sp.qpp, sp.Lq - q0);
         if (cnt < 0) cnt = 0;
     };
     if (STAGE && u_lo < u_hi) {
-        long long nm; int q0, cnt;
+        int nm, q0, cnt;
         pass_range(u_lo, nm, q0, cnt);
         stage_meta(meta0, loc, attn, sp, LP, nm, q0, cnt, fused ? refs0 : nullptr, ref, rpw);
     }
-    for (long long u = u_lo; u < u_hi; ++u) {
-        long long nm; int q0, cnt;
+    for (int u = u_lo; u < u_hi; ++u) {
+        int nm, q0, cnt;
         pass_range(u, nm, q0, cnt);
         const TM *meta = meta0 + ((u - u_lo) & 1) * meta_stride;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -289,7 +291,7 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
         }
         if (STAGE) {  // prefetch the next pass's metadata while this one computes (always one group, possibly empty)
             if (u + 1 < u_hi) {
-                long long nm2; int q02, cnt2;
+                int nm2, q02, cnt2;
                 pass_range(u + 1, nm2, q02, cnt2);
                 stage_meta(meta0 + ((u + 1 - u_lo) & 1) * meta_stride, loc, attn, sp, LP, nm2, q02, cnt2,
                            fused ? refs0 + ((u + 1 - u_lo) & 1) * ref_stride : nullptr, ref, rpw);
@@ -300,7 +302,7 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
         const bool live = ql < cnt;
         const int q = q0 + ql;
         const long long n = nm / sp.M;
-        const int m = (int)(nm - n * sp.M);
+        const int m = nm - (int)n * sp.M;
         const long long qm = (n * sp.Lq + q) * sp.M + m;
         using TM2 = typename Pair<TM>::type;
         const TM2 *loc2 = STAGE ? reinterpret_cast<const TM2 *>(meta + ql * 3 * LP) : reinterpret_cast<const TM2 *>(loc) + qm * LP;
@@ -390,7 +392,7 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
                 __syncthreads();
                 if (fused && mask != nullptr) {  // padding mask folded in (ms_deform_attn.py:103-104): masked pixels read as zero rows
                     const int W = sp.W[l], npix = sp.H[l] * W;
-                    const unsigned char *mk = mask + (nm / sp.M) * sp.S + sp.start[l];
+                    const unsigned char *mk = mask + (long long)(nm / sp.M) * sp.S + sp.start[l];
                     float4 *lv = slab + (size_t)(sp.prow0[l] + (W + 2) + 1) * 8;
                     for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
                         if (mk[pix]) {
@@ -510,6 +512,7 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
     const int max_threads = split == 4 ? 768 : 512;
     plan_passes(p.Lq, slabs, grid, max_threads / split, sp.qpp, sp.pps);
     sp.units = slabs * sp.pps;
+    if (sp.units >= (1LL << 30)) return false;  // 32-bit unit arithmetic in the kernel
     threads = ((sp.qpp * split + 31) / 32) * 32;
     if (threads > max_threads) threads = max_threads;
     // metadata staging (two buffers of qpp rows of 3*L*P floats) when 16-byte pieces line up and it fits
