@@ -123,7 +123,7 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
     const int Lq = sp.Lq, P = P_T > 0 ? P_T : sp.P, EP = Lq * P, LP = sp.L * P;
     float4 *V4 = smem4;                                   // zero-padded value slab of the current level: (H+2) x (W+2) rows
     float4 *ent = smem4 + (size_t)sp.vrows_max * 8;       // sorted samples: {lh, lw, attn, cell<<20 | p<<16 | q}
-    int *cell_off = reinterpret_cast<int *>(ent + EP);    // kMaxCells + 1 counters -> exclusive offsets
+    int *cell_off = reinterpret_cast<int *>(ent + EP + 4);  // (four spare entries, see the prefetch) kMaxCells + 1 counters -> exclusive offsets
     int *warp_tot = cell_off + kMaxCells + 8;
     constexpr bool GRING = (MODE & 1) != 0, DEFER = (MODE & 2) != 0, FUSED = (MODE & 4) != 0;
     // MODE bit 4 (16): fewer FMA-pipe instructions per sample -- four dot products of grad_out with (V00, dW, dH, dd) combined after
@@ -290,7 +290,13 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                 if (i < cells) cell_off[i] = base;
                 base += v[k];
             }
-            if (tid == kThreads - 1) cell_off[kMaxCells] = warp_tot[kThreads / 32 - 1];  // number of in-range samples
+            if (tid == kThreads - 1) {
+                const int tot = warp_tot[kThreads / 32 - 1];
+                cell_off[kMaxCells] = tot;  // number of in-range samples
+                // the grad_out prefetch runs up to four entries past a group's range without clamping: past the list's end it must
+                // still find a valid query index (0)
+                for (int k = 0; k < 4; ++k) ent[tot + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         __syncthreads();
 
@@ -404,7 +410,7 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         // slot `si` (GRING; one cp.async group per call) or into the register set g
         auto issue_g = [&](int e2, int si, float4 (&g)[CH]) {
             unsigned packed;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(ent_s + min(e2, e_hi - 1) * 16 + 12));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(ent_s + e2 * 16 + 12));
             // 64-bit base + unsigned 32-bit byte offset: two adds instead of a sign-extended 64-bit multiply-shift chain
             const TV *gq = reinterpret_cast<const TV *>(reinterpret_cast<const char *>(gobase) + (packed & 0xffff) * grow_b);
             if (GRING) {
@@ -645,7 +651,7 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
     }
     sp.units = (long long)p.N * p.M * p.L;
     if (sp.units >= (1LL << 30)) return false;  // 32-bit unit arithmetic in the kernel
-    smem = (size_t)sp.vrows_max * 8 * 16 + (size_t)p.Lq * p.P * 16 + (kMaxCells + 8 + 32) * sizeof(int) + kMaxCells * sizeof(int2);
+    smem = (size_t)sp.vrows_max * 8 * 16 + ((size_t)p.Lq * p.P + 4) * 16 + (kMaxCells + 8 + 32) * sizeof(int) + kMaxCells * sizeof(int2);
     if (smem > (size_t)p.smem_optin) return false;
     // three private 16-byte slots per chunk per thread for the cp.async grad_out pipeline, when they fit
     const int split = sorted_split();
