@@ -455,6 +455,12 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
 void plan_passes(int Lq, long long slabs, int ctas, int max_pairs, int &qpp, int &pps)
 {
     const int min_pps = (Lq + max_pairs - 1) / max_pairs;
+    static const int forced = [] { const char *e = getenv("MSDA_SLAB_PPS"); return e ? atoi(e) : 0; }();  // A/B switch
+    if (forced >= min_pps) {
+        pps = forced;
+        qpp = (Lq + forced - 1) / forced;
+        return;
+    }
     double best = 1e300;
     qpp = (Lq + min_pps - 1) / min_pps;
     pps = min_pps;

@@ -14,7 +14,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from .functions import MSDeformAttnFunction, MSDeformAttnPrologueFunction, fused_prologue_supported
+from .functions import MSDeformAttnFunction, MSDeformAttnPrologueFunction, _host_geometry, fused_prologue_supported
 
 
 def _is_power_of_2(n):
@@ -73,7 +73,12 @@ class MSDeformAttn(nn.Module):
         Returns [N, Lq, C].  (ms_deform_attn.py:86-129)"""
         N, Len_q, _ = query.shape
         N, Len_in, _ = input_flatten.shape
-        assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
+        # the reference's check (ms_deform_attn.py:100) reads a device scalar on every call -- a host synchronisation per layer, and
+        # illegal under CUDA-graph capture; on CUDA the same comparison runs on the cached host mirror of the geometry tensors
+        if input_spatial_shapes.is_cuda:
+            assert sum(h * w for h, w in _host_geometry(input_spatial_shapes, input_level_start_index)[2]) == Len_in
+        else:
+            assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
         value = self.value_proj(input_flatten).view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         sampling_offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)

@@ -67,6 +67,8 @@ def main():
     ref_ext = build_ref.load_ref()
     arms = [("fused", True, None), ("unfused", False, None)] + ([("reference", False, ref_ext)] if ref_ext is not None else [])
     arms.append(("fused_tf32_matmul", True, None))  # information only: NOT the reference's numerics (it runs strict-fp32 GEMMs)
+    if world == 1:  # the whole training step (forward, backward, AdamW) captured once in a CUDA graph and replayed
+        arms.append(("fused_graph", True, None))
     original = pkg_modules.MSDeformAttnFunction
     for name, fuse, ext in arms:
         torch.manual_seed(7)
@@ -87,7 +89,8 @@ def main():
         _RefFunction.ext = ext
         pkg_modules.MSDeformAttnFunction = _RefFunction if ext is not None else original
         model = torch.nn.parallel.DistributedDataParallel(top, device_ids=[local]) if world > 1 else top
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+        graphed = name.endswith("_graph")
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True, capturable=graphed)
         inputs = [x.clone().requires_grad_(True) for x in srcs]
         fin = {k: v.clone().requires_grad_(True) for k, v in feats.items()} if decoder else None
 
@@ -105,15 +108,27 @@ def main():
                 memory.backward(gmem)
             opt.step()
 
+        run = step
+        if graphed:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            run = graph.replay
         for _ in range(5):
-            step()
+            run()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
         l0 = pkg.launch_count()
         for a, b in evs:
-            a.record(); step(); b.record()
+            a.record(); run(); b.record()
         torch.cuda.synchronize()
         ms = statistics.median(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([ms], device=dev)
@@ -121,6 +136,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         res["arms"][name] = {"ms_per_step": ms, "frames_per_s": world * frames / (ms * 1e-3), "msda_launches_per_step": (pkg.launch_count() - l0) / iters}
+        if graphed:
+            del graph, run
         del model, enc, top, opt
     pkg_modules.MSDeformAttnFunction = original
     torch.backends.cuda.matmul.allow_tf32 = False
