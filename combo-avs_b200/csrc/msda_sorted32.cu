@@ -341,8 +341,9 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(att2 + q * qstride));
             }
             const TV *v2 = value + (n2 * sp.S + sp.start[l2]) * (long long)pix + (long long)m2 * kD;
-            for (int i = tid; i < sp.H[l2] * sp.W[l2]; i += kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(v2 + i * pix));
-            if (l2 == 0) {
+            if (sp.prefetch == 1)
+                for (int i = tid; i < sp.H[l2] * sp.W[l2]; i += kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(v2 + i * pix));
+            if (sp.prefetch == 1 && l2 == 0) {
                 const TV *g2p = grad_out + (n2 * Lq * sp.M + m2) * (long long)kD;
                 for (int q = tid; q < Lq; q += kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(g2p + q * pix));
             }
@@ -621,9 +622,9 @@ int sorted_mode()  // bit 0: cp.async grad_out ring, bit 1: deferred reduction, 
     static const int v = [] { const char *e = getenv("MSDA_SORTED_MODE"); return e ? atoi(e) & 19 : 16; }();
     return v;
 }
-bool sorted_prefetch()
+int sorted_prefetch()
 {
-    static const bool v = [] { const char *e = getenv("MSDA_SORTED_PF"); return e && atoi(e) == 1; }();
+    static const int v = [] { const char *e = getenv("MSDA_SORTED_PF"); const int x = e ? atoi(e) : 0; return x == 1 || x == 2 ? x : 0; }();  // 2: locations / weights only
     return v;
 }
 
@@ -659,7 +660,7 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
     mode = sorted_mode();
     if (smem + gring > (size_t)p.smem_optin) mode &= ~1;
     if (mode & 1) smem += gring;
-    sp.prefetch = sorted_prefetch() ? 1 : 0;
+    sp.prefetch = sorted_prefetch();
     sp.fused = p.ref != nullptr ? 1 : 0;
     if (sp.fused && p.loc_dtype != 0) return false;
     if (sp.fused) mode &= 16;
