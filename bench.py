@@ -282,7 +282,8 @@ def run_ours(args):
     dom = ("backward", bytes_b, us_b) if us_b >= us_f else ("forward", bytes_f, us_f)
     achieved = dom[1] / (dom[2] * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "%s (%s)" % (dom[0], pkg.last_variant(dom[0])), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": (load_traffic(pkg.last_variant(dom[0])) or {}).get("dram_bytes_per_launch") if args.dtype == "fp32" and nF == 40 else None,
+                "frac": achieved / peak, "traffic": (load_traffic(pkg.last_variant(dom[0]) + ("" if args.dtype == "fp32" else "_bf16")) or {}).get("dram_bytes_per_launch")
+                if nF == 40 and (args.dtype == "fp32" or loc_dtype == torch.float32) else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom[1], "us_per_launch": dom[2],
                 "fwd": {"us": us_f, "bytes": bytes_f, "GBps": bytes_f / us_f / 1e3, "frac": bytes_f / us_f / 1e3 / peak, "variant": pkg.last_variant("forward")},
