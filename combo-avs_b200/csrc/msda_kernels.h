@@ -21,6 +21,7 @@ struct Problem {
     LevelTable table;  // valid iff have_host
     int sm_count;
     int smem_optin;    // max dynamic shared memory per block (opt-in)
+    int device = 0;    // CUDA ordinal the pointers live on (per-device one-time kernel attribute setup)
     // fused module prologue (ops/modules/ms_deform_attn.py:102-116): when `ref` is set, `loc` holds the raw sampling OFFSETS and
     // locations are ref + offset / (W_l, H_l); in the forward `attn` then holds the raw attention LOGITS (softmax over L*P is
     // taken in the kernel and written to `attn_out`), in the backward it holds the softmaxed weights saved by the forward.
@@ -59,10 +60,13 @@ cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st);
 bool sorted32_supported(const Problem &p);
 cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st);
 
-// pipe32: sorted32's design with the sort of unit u+1 overlapped with the walk of unit u (msda_pipe32.cu)
-bool pipe32_supported(const Problem &p);
-size_t bwd_pipe32_workspace(int dtype, int D, int Lq, int P);
-cudaError_t bwd_pipe32(const Problem &p, const BackwardIO &io, cudaStream_t st);
+// split32: the backward as two kernels on different pipes -- gather32 (grad_sampling_loc / grad_attn_weight by the forward's
+// shared-memory gather, TMA-staged slabs; msda_slab32.cu) and scatter32 (grad_value by sort-and-segment; msda_scatter32.cu,
+// accumulates into a zeroed grad_value)
+bool gather32_supported(const Problem &p);
+cudaError_t bwd_gather32(const Problem &p, const BackwardIO &io, cudaStream_t st);
+bool scatter32_supported(const Problem &p);
+cudaError_t bwd_scatter32(const Problem &p, const BackwardIO &io, cudaStream_t st);
 
 // zero the rows of grad[rows][row_elems] whose mask byte is set (masked_fill backward, ms_deform_attn.py:103-104)
 cudaError_t zero_masked_rows(float *grad, const unsigned char *mask, long long rows, int row_elems, int sm_count, cudaStream_t st);

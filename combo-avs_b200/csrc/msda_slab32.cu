@@ -14,10 +14,13 @@
 // Scheduling: work unit = (slab, pass) where a pass is a contiguous block of <= QPP queries; the host picks the
 // number of passes per slab that balances N*M*passes units over the SMs; each persistent CTA (one per SM) owns a
 // contiguous unit range, so consecutive units reuse the resident slab.
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "msda_kernels.h"
+#include "msda_tma.cuh"
 
 namespace msda {
 namespace {
@@ -451,6 +454,329 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// TMA-pipelined slab kernel (float32 values and metadata): the default forward, and -- BWD -- the gather half of the split
+// backward (grad_sampling_loc / grad_attn_weight; ms_deform_im2col_cuda.cuh:92-164 without the grad_value scatter, which
+// msda_scatter32.cu does by sort-and-segment).
+//
+// Same mapping, metadata staging and scheduling as fwd_slab32_kernel above.  What changes is how slabs move:
+//   * the last warp is a PRODUCER: one elected lane issues one cp.async.bulk.tensor per level (a (H+2) x (W+2) pixel box at
+//     (-1, -1); the out-of-bounds border arrives as zeros) and goes back to waiting; nobody computes addresses, nobody zero-fills;
+//   * full[l] / empty[l] mbarriers per level hand the level regions back and forth.  Consumers release level l of the resident
+//     slab as soon as their last pass is past it, so the next slab's small levels land while the 28x28 level is still being
+//     gathered, and its 28x28 level lands under the first pass's small levels -- the slab switch that the cp.async version
+//     serialises (a CTA barrier, 158 KB at the per-SM fill rate, another barrier per level) mostly disappears.
+// BWD: a lane pair holds the grad_output row of its (query, head) in registers (16 channels per lane), forms four dot products
+// with the neighbour rows per sample, combines them with the bilinear weights after the horizontal add, exchanges three partial
+// sums with its partner (one shuffle each) and writes the results IN PLACE over the staged locations / weights of its row; each
+// warp then streams its rows out with 16-byte stores (every 32-byte sector of grad_loc / grad_attn is written exactly once).
+struct alignas(64) TmaMaps {
+    CUtensorMap level[4];
+};
+constexpr int kTmaMaxLevels = 4;
+constexpr int kFwdTmaThreads = 512, kBwdTmaThreads = 416;  // including the producer warp
+
+template <int P_T, bool BWD>
+__global__ void __launch_bounds__(BWD ? kBwdTmaThreads : kFwdTmaThreads, 1)
+slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn, float *__restrict__ out,
+                  const float *__restrict__ grad_out, float *__restrict__ grad_loc, float *__restrict__ grad_attn,
+                  const float *__restrict__ ref, float *__restrict__ attn_out, const unsigned char *__restrict__ mask,
+                  const __grid_constant__ SlabParams sp, const __grid_constant__ TmaMaps maps)
+{
+    constexpr int CH = 4;  // SPLIT = 2: a lane owns four 16-byte chunks (16 channels)
+    extern __shared__ __align__(128) float4 slab[];
+    const int P = P_T > 0 ? P_T : sp.P;
+    const int LP = sp.L * P;
+    float *meta0 = reinterpret_cast<float *>(slab + (size_t)sp.padded_rows * 8);  // two staging buffers of qpp rows
+    const int meta_stride = sp.qpp * 3 * LP;
+    float *refs0 = meta0 + 2 * meta_stride;
+    const int ref_stride = sp.qpp * sp.L * 2;
+    const bool fused = sp.fused != 0;
+    const int ref_floats = fused ? 2 * ref_stride : 0;
+    const unsigned bars = (unsigned)__cvta_generic_to_shared(refs0 + ref_floats);  // full[l] at bars + 8*l, empty[l] at bars + 8*(4 + l)
+    const int nwarps = blockDim.x >> 5, ncw = nwarps - 1, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u_lo = (int)(sp.units * blockIdx.x / gridDim.x), u_hi = (int)(sp.units * (blockIdx.x + 1) / gridDim.x);
+    if (u_lo >= u_hi) return;
+    const int nm_first = u_lo / sp.pps, nm_last = (u_hi - 1) / sp.pps;
+    if (threadIdx.x == 0) {
+        for (int l = 0; l < sp.L; ++l) {
+            mbar_init(bars + 8 * l, 1);
+            mbar_init(bars + 8 * (kTmaMaxLevels + l), ncw);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    unsigned slab_s = (unsigned)__cvta_generic_to_shared(slab);
+
+    if (wid == ncw) {  // ---- producer warp ------------------------------------------------------------------------------------
+        if (lane == 0) {
+            for (int l = 0; l < sp.L; ++l) tma_prefetch_map(&maps.level[l]);
+            int it = 0;
+            for (int nm = nm_first; nm <= nm_last; ++nm, ++it) {
+                const int n = nm / sp.M, m = nm - n * sp.M;
+                for (int l = 0; l < sp.L; ++l) {
+                    if (it > 0) mbar_wait(bars + 8 * (kTmaMaxLevels + l), (unsigned)((it - 1) & 1));  // consumers are past level l of the previous slab
+                    const unsigned bytes = (unsigned)((sp.H[l] + 2) * (sp.W[l] + 2)) * kRowBytes;
+                    mbar_arrive_expect_tx(bars + 8 * l, bytes);
+                    tma_load_5d(slab_s + (unsigned)sp.prow0[l] * kRowBytes, &maps.level[l], bars + 8 * l, 0, m, -1, -1, n);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumer warps --------------------------------------------------------------------------------------------------------
+    const int ncons = ncw * 32;
+    constexpr int rpw = 16;  // (query, head) rows per warp
+    int ql = threadIdx.x >> 1;
+    const int part = threadIdx.x & 1;
+    pin(ql);
+    unsigned off[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        off[k] = (part * CH + ((k + ql) % CH)) * 16;
+        pin(off[k]);
+    }
+    pin(slab_s);
+    auto pass_range = [&](int u, int &nm, int &q0, int &cnt) {
+        nm = u / sp.pps;
+        q0 = (u - nm * sp.pps) * sp.qpp;
+        cnt = min(sp.qpp, sp.Lq - q0);
+        if (cnt < 0) cnt = 0;
+    };
+    {
+        int nm, q0, cnt;
+        pass_range(u_lo, nm, q0, cnt);
+        stage_meta(meta0, loc, attn, sp, LP, nm, q0, cnt, fused ? refs0 : (float *)nullptr, ref, rpw);
+    }
+    int it = 0, resident = nm_first;
+    for (int u = u_lo; u < u_hi; ++u) {
+        int nm, q0, cnt;
+        pass_range(u, nm, q0, cnt);
+        const bool fresh = u == u_lo || nm != resident;  // first pass on this slab: its levels arrive on full[l]
+        if (nm != resident) {
+            resident = nm;
+            ++it;
+        }
+        const bool release = nm != nm_last && (u + 1 - nm * sp.pps) == sp.pps;  // last pass on a slab that is followed by another
+        float *meta = meta0 + ((u - u_lo) & 1) * meta_stride;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (u + 1 < u_hi) {  // prefetch the next pass's metadata while this one computes
+            int nm2, q02, cnt2;
+            pass_range(u + 1, nm2, q02, cnt2);
+            stage_meta(meta0 + ((u + 1 - u_lo) & 1) * meta_stride, loc, attn, sp, LP, nm2, q02, cnt2,
+                       fused ? refs0 + ((u + 1 - u_lo) & 1) * ref_stride : (float *)nullptr, ref, rpw);
+        }
+        const bool live = ql < cnt;
+        const int q = q0 + ql;
+        const long long n = nm / sp.M;
+        const int m = nm - (int)n * sp.M;
+        const long long qm = (n * sp.Lq + q) * sp.M + m;
+        float *row = meta + ql * 3 * LP;
+        const float2 *loc2 = reinterpret_cast<const float2 *>(row);
+        const float *att = row + 2 * LP;
+        float4 g[CH];
+        if (BWD) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) g[k] = live ? ldg4(grad_out + qm * kD + (off[k] >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (fused) {
+            // Module prologue in place on the staged row (ops/modules/ms_deform_attn.py:102-116); the two lanes of the pair run one
+            // instruction stream on the two halves of the row.  Forward: softmax over the L*P logits (max and sum exchanged with one
+            // shuffle each; ex2-based exp, one reciprocal) and location = reference point + offset * (1/W_l, 1/H_l) (one FMA).
+            // Backward: the weights arrive softmaxed (saved by the forward); only the locations are rebuilt, with the same FMA.
+            const int hl = LP >> 1;  // LP % 4 == 0
+            float *lg = row + 2 * LP + part * hl;
+            const float *rf = refs0 + ((u - u_lo) & 1) * ref_stride + ql * sp.L * 2;
+            if (!BWD && LP == 12 && P == 4) {
+                // the production shape (3 levels x 4 points): the lane's half row lives in registers, vector loads / stores only
+                float2 g0 = make_float2(0.f, 0.f), g1 = g0, g2 = g0;
+                float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0;
+                float4 *xy4 = reinterpret_cast<float4 *>(row) + part * 3;
+                if (live) {
+                    g0 = reinterpret_cast<const float2 *>(lg)[0]; g1 = reinterpret_cast<const float2 *>(lg)[1]; g2 = reinterpret_cast<const float2 *>(lg)[2];
+                    o0 = xy4[0]; o1 = xy4[1]; o2 = xy4[2];
+                }
+                float mx = fmaxf(fmaxf(fmaxf(g0.x, g0.y), fmaxf(g1.x, g1.y)), fmaxf(g2.x, g2.y));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                g0.x = __expf(g0.x - mx); g0.y = __expf(g0.y - mx); g1.x = __expf(g1.x - mx);
+                g1.y = __expf(g1.y - mx); g2.x = __expf(g2.x - mx); g2.y = __expf(g2.y - mx);
+                float sum = (g0.x + g0.y) + (g1.x + g1.y) + (g2.x + g2.y);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                if (live) {
+                    const float inv = __frcp_rn(sum);
+                    g0.x *= inv; g0.y *= inv; g1.x *= inv; g1.y *= inv; g2.x *= inv; g2.y *= inv;
+                    reinterpret_cast<float2 *>(lg)[0] = g0; reinterpret_cast<float2 *>(lg)[1] = g1; reinterpret_cast<float2 *>(lg)[2] = g2;
+                    float2 *ao = reinterpret_cast<float2 *>(attn_out + qm * LP + part * hl);
+                    ao[0] = g0; ao[1] = g1; ao[2] = g2;
+                    // samples part*6 .. part*6+5: part 0 -> levels 0,0,0,0,1,1; part 1 -> levels 1,1,2,2,2,2
+                    const int la = part, lb = part + 1;
+                    const float wa = sp.rw[la], ha = sp.rh[la], wb = sp.rw[lb], hb = sp.rh[lb];
+                    const float xa = rf[2 * la], ya = rf[2 * la + 1], xb = rf[2 * lb], yb = rf[2 * lb + 1];
+                    const bool p0 = part == 0;  // the middle float4 (samples 2, 3 of the half) belongs to level a for part 0, b for part 1
+                    o0.x = __fmaf_rn(o0.x, wa, xa); o0.y = __fmaf_rn(o0.y, ha, ya); o0.z = __fmaf_rn(o0.z, wa, xa); o0.w = __fmaf_rn(o0.w, ha, ya);
+                    o1.x = __fmaf_rn(o1.x, p0 ? wa : wb, p0 ? xa : xb); o1.y = __fmaf_rn(o1.y, p0 ? ha : hb, p0 ? ya : yb);
+                    o1.z = __fmaf_rn(o1.z, p0 ? wa : wb, p0 ? xa : xb); o1.w = __fmaf_rn(o1.w, p0 ? ha : hb, p0 ? ya : yb);
+                    o2.x = __fmaf_rn(o2.x, wb, xb); o2.y = __fmaf_rn(o2.y, hb, yb); o2.z = __fmaf_rn(o2.z, wb, xb); o2.w = __fmaf_rn(o2.w, hb, yb);
+                    xy4[0] = o0; xy4[1] = o1; xy4[2] = o2;
+                }
+            } else {
+                if (!BWD) {
+                    float mx = -3.0e38f;
+                    if (live)
+                        for (int i = 0; i < hl; ++i) mx = fmaxf(mx, lg[i]);
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    float sum = 0.f;
+                    if (live)
+                        for (int i = 0; i < hl; ++i) {
+                            const float e = __expf(lg[i] - mx);
+                            lg[i] = e;
+                            sum += e;
+                        }
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    if (live) {
+                        const float inv = __frcp_rn(sum);
+                        float2 *ao = reinterpret_cast<float2 *>(attn_out + qm * LP + part * hl);
+                        for (int i = 0; i < hl; i += 2) {
+                            const float2 a2 = make_float2(lg[i] * inv, lg[i + 1] * inv);
+                            *reinterpret_cast<float2 *>(lg + i) = a2;
+                            ao[i >> 1] = a2;
+                        }
+                    }
+                }
+                if (live) {
+                    float2 *xy = reinterpret_cast<float2 *>(row) + part * hl;
+                    for (int i = 0; i < hl; ++i) {
+                        const int l = (part * hl + i) / P;
+                        float2 v = xy[i];
+                        v.x = __fmaf_rn(v.x, sp.rw[l], rf[2 * l]);
+                        v.y = __fmaf_rn(v.y, sp.rh[l], rf[2 * l + 1]);
+                        xy[i] = v;
+                    }
+                }
+            }
+            __syncwarp();  // both lanes of a pair read the whole row below
+        }
+        f4p acc[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) acc[k].lo = acc[k].hi = make_float2(0.f, 0.f);
+        for (int l = 0; l < sp.L; ++l) {
+            if (fresh) {
+                mbar_wait(bars + 8 * l, (unsigned)(it & 1));  // level l of this slab has landed (border included)
+                if (fused && mask != nullptr) {  // padding mask folded in (ms_deform_attn.py:103-104): masked pixels read as zero rows
+                    const int W = sp.W[l], npix = sp.H[l] * W;
+                    const unsigned char *mk = mask + n * sp.S + sp.start[l];
+                    float4 *lv = slab + (size_t)(sp.prow0[l] + (W + 2) + 1) * 8;
+                    for (int pix = threadIdx.x; pix < npix; pix += ncons) {
+                        if (mk[pix]) {
+                            const int y = (int)__umulhi((unsigned)pix, sp.wrecip[l]), x = pix - y * W;
+                            float4 *prow = lv + (size_t)(y * (W + 2) + x) * 8;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) prow[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                    fence_proxy_async();  // these generic-proxy writes precede the next TMA fill of the region
+                    asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+                }
+            }
+            if (live) {
+                const float Hf = (float)sp.H[l], Wf = (float)sp.W[l];
+                const float hmax = sp.hmax[l], wmax = sp.wmax[l];
+                const int pitch = sp.W[l] + 2;
+                const unsigned lvl_s = slab_s + (unsigned)(sp.prow0[l] + pitch + 1) * kRowBytes;  // address of pixel (0,0)
+                const unsigned pitch_b = (unsigned)pitch * kRowBytes;
+                const float sx = fused ? 1.f : Wf, sy = fused ? 1.f : Hf;  // d(loc)/d(offset) = 1/(W, H) cancels the (W, H) of cuh:126-127
+#pragma unroll
+                for (int pp = 0; pp < (P_T > 0 ? P_T : 1); ++pp) {
+                    for (int p = (P_T > 0 ? pp : 0); p < (P_T > 0 ? pp + 1 : P); ++p) {
+                        const int s = l * P + p;
+                        const float2 xy = loc2[s];
+                        const float a_in = att[s];
+                        const float h = __fmaf_rn(xy.y, Hf, -0.5f), w = __fmaf_rn(xy.x, Wf, -0.5f);
+                        const bool ok = h > -1.f && w > -1.f && h < Hf && w < Wf;
+                        const float hc = fminf(fmaxf(h, -1.f), hmax), wc = fminf(fmaxf(w, -1.f), wmax);
+                        float fh, fw;
+                        int y0, x0;
+                        floor_split(hc, fh, y0);
+                        floor_split(wc, fw, x0);
+                        const float lh = hc - fh, lw = wc - fw;
+                        const unsigned r00 = lvl_s + (unsigned)(y0 * pitch + x0) * kRowBytes;
+                        const unsigned r10 = r00 + pitch_b;
+                        if (!BWD) {
+                            const float a = ok ? a_in : 0.f;
+                            const float ahh = a * (1.f - lh), alh = a * lh, hw = 1.f - lw;
+                            const float w1s = ahh * hw, w2s = ahh * lw, w3s = alh * hw, w4s = alh * lw;
+                            const float2 w1 = make_float2(w1s, w1s), w2 = make_float2(w2s, w2s), w3 = make_float2(w3s, w3s), w4 = make_float2(w4s, w4s);
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) {
+                                const float4 v1 = lds4(r00 + off[k]), v2 = lds4(r00 + off[k] + kRowBytes);
+                                const float4 v3 = lds4(r10 + off[k]), v4 = lds4(r10 + off[k] + kRowBytes);
+                                acc[k].lo = __ffma2_rn(w1, make_float2(v1.x, v1.y), __ffma2_rn(w2, make_float2(v2.x, v2.y),
+                                            __ffma2_rn(w3, make_float2(v3.x, v3.y), __ffma2_rn(w4, make_float2(v4.x, v4.y), acc[k].lo))));
+                                acc[k].hi = __ffma2_rn(w1, make_float2(v1.z, v1.w), __ffma2_rn(w2, make_float2(v2.z, v2.w),
+                                            __ffma2_rn(w3, make_float2(v3.z, v3.w), __ffma2_rn(w4, make_float2(v4.z, v4.w), acc[k].hi))));
+                            }
+                        } else {
+                            float2 d1 = make_float2(0.f, 0.f), d2 = d1, d3 = d1, d4 = d1;  // lane-partial dot products of g with the four neighbours
+#pragma unroll
+                            for (int k = 0; k < CH; ++k) {
+                                const float4 v1 = lds4(r00 + off[k]), v2 = lds4(r00 + off[k] + kRowBytes);
+                                const float4 v3 = lds4(r10 + off[k]), v4 = lds4(r10 + off[k] + kRowBytes);
+                                const float2 glo = make_float2(g[k].x, g[k].y), ghi = make_float2(g[k].z, g[k].w);
+                                d1 = __ffma2_rn(ghi, make_float2(v1.z, v1.w), __ffma2_rn(glo, make_float2(v1.x, v1.y), d1));
+                                d2 = __ffma2_rn(ghi, make_float2(v2.z, v2.w), __ffma2_rn(glo, make_float2(v2.x, v2.y), d2));
+                                d3 = __ffma2_rn(ghi, make_float2(v3.z, v3.w), __ffma2_rn(glo, make_float2(v3.x, v3.y), d3));
+                                d4 = __ffma2_rn(ghi, make_float2(v4.z, v4.w), __ffma2_rn(glo, make_float2(v4.x, v4.y), d4));
+                            }
+                            const float s1 = d1.x + d1.y, s2 = d2.x + d2.y, s3 = d3.x + d3.y, s4 = d4.x + d4.y;
+                            const float hh = 1.f - lh, hw = 1.f - lw;
+                            // cuh:104-160: val = sum_i w_i v_i; grad_w = hh (v2 - v1) + lh (v4 - v3); grad_h = hw (v3 - v1) + lw (v4 - v2)
+                            float ga = hh * (hw * s1 + lw * s2) + lh * (hw * s3 + lw * s4);
+                            float gw = hh * (s2 - s1) + lh * (s4 - s3);
+                            float gh = hw * (s3 - s1) + lw * (s4 - s2);
+                            ga += __shfl_xor_sync(0xffffffffu, ga, 1);
+                            gw += __shfl_xor_sync(0xffffffffu, gw, 1);
+                            gh += __shfl_xor_sync(0xffffffffu, gh, 1);
+                            // a sample outside the map has exactly zero gradients (cuh:352-356), whatever the clamped rows hold
+                            if (part == 0) row[2 * LP + s] = ok ? ga : 0.f;
+                            else reinterpret_cast<float2 *>(row)[s] = ok ? make_float2(sx * a_in * gw, sy * a_in * gh) : make_float2(0.f, 0.f);
+                        }
+                    }
+                }
+            }
+            if (release) {  // this warp is done with level l of the resident slab: the producer may refill it
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + 8 * (kTmaMaxLevels + l));
+            }
+        }
+        if (!BWD) {
+            if (live) {
+                float *o = out + qm * kD;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) store4(o + (off[k] >> 2), make_float4(acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y));
+            }
+        } else {
+            // stream this warp's rows out: per row 2*LP grad_loc floats, then LP grad_attn floats, as 16-byte pieces
+            __syncwarp();
+            const int r0 = wid * rpw, nrows = min(max(cnt - r0, 0), rpw);
+            const int pieces = (3 * LP) >> 2, loc_pieces = LP >> 1;
+            const long long qm0 = ((long long)(nm / sp.M) * sp.Lq + q0 + r0) * sp.M + m;
+            float *lbase = grad_loc + qm0 * (2 * LP), *abase = grad_attn + qm0 * LP;
+            const int lstride = sp.M * 2 * LP, astride = sp.M * LP;
+            const float *mrow = meta + r0 * (3 * LP);
+            for (int i = lane; i < nrows * pieces; i += 32) {
+                const int rq = (int)__umulhi((unsigned)i, sp.precip), pc = i - rq * pieces;
+                const float4 v = *reinterpret_cast<const float4 *>(mrow + rq * (3 * LP) + pc * 4);
+                float *dst = pc < loc_pieces ? lbase + rq * lstride + pc * 4 : abase + rq * astride + (pc - loc_pieces) * 4;
+                *reinterpret_cast<float4 *>(dst) = v;
+            }
+            __syncwarp();  // the rows are re-staged two passes from now by this warp's own cp.async
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // choose passes-per-slab so that N*M*pps units spread evenly over `ctas` persistent CTAs
 void plan_passes(int Lq, long long slabs, int ctas, int max_pairs, int &qpp, int &pps)
 {
@@ -477,21 +803,9 @@ void plan_passes(int Lq, long long slabs, int ctas, int max_pairs, int &qpp, int
     }
 }
 
-int slab_split()
+// plan shared by the cp.async kernel and the TMA kernel; `max_threads` bounds the lanes that gather (two per query)
+bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &threads, int &grid, bool &stage, int max_threads)
 {
-    static const int v = [] { const char *e = getenv("MSDA_SLAB_SPLIT"); return e && atoi(e) == 4 ? 4 : 2; }();
-    return v;
-}
-
-bool slab_wstage()
-{
-    static const bool v = [] { const char *e = getenv("MSDA_SLAB_WSTAGE"); return !(e && atoi(e) == 0); }();
-    return v;
-}
-
-bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &threads, int &grid, bool &stage)
-{
-    const int split = slab_split();
     if (!((p.dtype == 0 || p.dtype == 1) && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
     sp.L = p.L; sp.P = p.P; sp.S = p.S; sp.M = p.M; sp.Lq = p.Lq;
     int rows = 0;
@@ -515,11 +829,10 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
     const long long slabs = (long long)p.N * p.M;
     grid = (int)(slabs * 16 < p.sm_count ? slabs * 16 : p.sm_count);
     if (grid < 1) grid = 1;
-    const int max_threads = split == 4 ? 768 : 512;
-    plan_passes(p.Lq, slabs, grid, max_threads / split, sp.qpp, sp.pps);
+    plan_passes(p.Lq, slabs, grid, max_threads / 2, sp.qpp, sp.pps);
     sp.units = slabs * sp.pps;
     if (sp.units >= (1LL << 30)) return false;  // 32-bit unit arithmetic in the kernel
-    threads = ((sp.qpp * split + 31) / 32) * 32;
+    threads = ((sp.qpp * 2 + 31) / 32) * 32;
     if (threads > max_threads) threads = max_threads;
     // metadata staging (two buffers of qpp rows of 3*L*P floats) when 16-byte pieces line up and it fits
     const int LP = p.L * p.P;
@@ -527,30 +840,85 @@ bool make_params(const Problem &p, SlabParams &sp, size_t &smem_bytes, int &thre
     const size_t meta_bytes = 2 * (size_t)sp.qpp * 3 * LP * (p.loc_dtype == 1 ? 2 : 4);
     stage = (LP % 4 == 0) && smem_bytes + meta_bytes <= (size_t)p.smem_optin;
     if (stage) smem_bytes += meta_bytes;
-    sp.wstage = (stage && slab_wstage()) ? 1 : 0;
+    sp.wstage = stage ? 1 : 0;  // every warp stages the rows of its own lanes
     sp.fused = 0;
     if (p.ref != nullptr) {  // fused prologue: needs the staged path, float32 metadata and room for the reference points
         const size_t ref_bytes = 2 * (size_t)sp.qpp * p.L * 2 * 4;
-        if (!stage || p.loc_dtype != 0 || split != 2 || smem_bytes + ref_bytes > (size_t)p.smem_optin || p.attn_out == nullptr) return false;
+        if (!stage || p.loc_dtype != 0 || smem_bytes + ref_bytes > (size_t)p.smem_optin) return false;
         smem_bytes += ref_bytes;
         sp.fused = 1;
     }
     return true;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is read-only state afterwards
+template <auto Kern> cudaError_t ensure_smem_optin(const Problem &p)
+{
+    static std::atomic<unsigned long long> done{0};
+    const unsigned long long bit = 1ULL << (p.device & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_optin);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
 template <typename TV, typename TM>
 cudaError_t launch_typed(const Problem &p, void *out, cudaStream_t st, const SlabParams &sp, size_t smem, int threads, int grid, bool stage)
 {
-    const bool s4 = slab_split() == 4;
-    auto kern = p.P == 4 ? (stage ? (s4 ? fwd_slab32_kernel<TV, TM, 4, true, 4> : fwd_slab32_kernel<TV, TM, 4, true, 2>)
-                                  : (s4 ? fwd_slab32_kernel<TV, TM, 4, false, 4> : fwd_slab32_kernel<TV, TM, 4, false, 2>))
-                         : (stage ? (s4 ? fwd_slab32_kernel<TV, TM, 0, true, 4> : fwd_slab32_kernel<TV, TM, 0, true, 2>)
-                                  : (s4 ? fwd_slab32_kernel<TV, TM, 0, false, 4> : fwd_slab32_kernel<TV, TM, 0, false, 2>));
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, threads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (TV *)out, (const TM *)p.ref, (TM *)p.attn_out, p.mask, sp);
-    count_launch();
-    return cudaGetLastError();
+    auto go = [&](auto kern_c) {
+        constexpr auto kern = decltype(kern_c)::value;
+        cudaError_t e = ensure_smem_optin<kern>(p);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, threads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (TV *)out, (const TM *)p.ref, (TM *)p.attn_out, p.mask, sp);
+        count_launch();
+        return cudaGetLastError();
+    };
+    using std::integral_constant;
+    if (p.P == 4) return stage ? go(integral_constant<decltype(&fwd_slab32_kernel<TV, TM, 4, true, 2>), &fwd_slab32_kernel<TV, TM, 4, true, 2>>())
+                               : go(integral_constant<decltype(&fwd_slab32_kernel<TV, TM, 4, false, 2>), &fwd_slab32_kernel<TV, TM, 4, false, 2>>());
+    return stage ? go(integral_constant<decltype(&fwd_slab32_kernel<TV, TM, 0, true, 2>), &fwd_slab32_kernel<TV, TM, 0, true, 2>>())
+                 : go(integral_constant<decltype(&fwd_slab32_kernel<TV, TM, 0, false, 2>), &fwd_slab32_kernel<TV, TM, 0, false, 2>>());
+}
+
+// The TMA kernel applies to float32 values + float32 metadata, L <= 4, L*P % 4 == 0, levels that fit a 256 x 256 box and a
+// 16-byte aligned value pointer; everything else keeps the cp.async kernel (forward) / the sorted backward.
+bool make_tma(const Problem &p, bool bwd, SlabParams &sp, size_t &smem, int &threads, int &grid, TmaMaps *maps)
+{
+    static const bool off = [] { const char *e = getenv("MSDA_SLAB_TMA"); return e && atoi(e) == 0; }();  // A/B switch
+    if (off || p.dtype != 0 || p.loc_dtype != 0 || p.L > kTmaMaxLevels) return false;
+    bool stage;
+    if (!make_params(p, sp, smem, threads, grid, stage, (bwd ? kBwdTmaThreads : kFwdTmaThreads) - 32) || !stage) return false;
+    if (!bwd && p.ref != nullptr && p.attn_out == nullptr) return false;
+    smem += 2 * kTmaMaxLevels * 8;  // full[l], empty[l]
+    if (smem > (size_t)p.smem_optin) return false;
+    threads += 32;  // the producer warp
+    for (int l = 0; l < p.L; ++l) {
+        if (sp.H[l] + 2 > 256 || sp.W[l] + 2 > 256) return false;
+        if (maps != nullptr &&
+            !tma_make_level_map(&maps->level[l], (const float *)p.value + (size_t)sp.start[l] * p.M * kD, p.N, p.S, p.M, sp.H[l], sp.W[l]))
+            return false;
+    }
+    if (maps == nullptr && (tma_encode_fn() == nullptr || (reinterpret_cast<uintptr_t>(p.value) & 15) != 0)) return false;
+    return true;
+}
+
+template <bool BWD>
+cudaError_t launch_tma(const Problem &p, void *out, const BackwardIO *io, cudaStream_t st, const SlabParams &sp, size_t smem, int threads,
+                       int grid, const TmaMaps &maps)
+{
+    auto go = [&](auto kern_c) {
+        constexpr auto kern = decltype(kern_c)::value;
+        cudaError_t e = ensure_smem_optin<kern>(p);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, threads, smem, st>>>((const float *)p.loc, (const float *)p.attn, (float *)out, io ? (const float *)io->grad_out : nullptr,
+                                          io ? (float *)io->grad_loc : nullptr, io ? (float *)io->grad_attn : nullptr, (const float *)p.ref,
+                                          (float *)p.attn_out, p.mask, sp, maps);
+        count_launch();
+        return cudaGetLastError();
+    };
+    using std::integral_constant;
+    if (p.P == 4) return go(integral_constant<decltype(&slab32_tma_kernel<4, BWD>), &slab32_tma_kernel<4, BWD>>());
+    return go(integral_constant<decltype(&slab32_tma_kernel<0, BWD>), &slab32_tma_kernel<0, BWD>>());
 }
 
 }  // namespace
@@ -561,7 +929,8 @@ bool slab32_supported(const Problem &p)
     size_t smem;
     int threads, grid;
     bool stage;
-    return make_params(p, sp, smem, threads, grid, stage);
+    if (!make_params(p, sp, smem, threads, grid, stage, 512)) return false;
+    return p.ref == nullptr || p.attn_out != nullptr;
 }
 
 cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st)
@@ -570,11 +939,36 @@ cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st)
     size_t smem;
     int threads, grid;
     bool stage;
-    if (!make_params(p, sp, smem, threads, grid, stage)) return cudaErrorInvalidValue;
     if ((long long)p.N * p.M * p.Lq == 0) return cudaSuccess;
+    {
+        TmaMaps maps;
+        if (make_tma(p, false, sp, smem, threads, grid, &maps)) return launch_tma<false>(p, out, nullptr, st, sp, smem, threads, grid, maps);
+    }
+    if (!make_params(p, sp, smem, threads, grid, stage, 512)) return cudaErrorInvalidValue;
+    if (p.ref != nullptr && p.attn_out == nullptr) return cudaErrorInvalidValue;
     return p.dtype == 0                    ? launch_typed<float, float>(p, out, st, sp, smem, threads, grid, stage)
            : p.loc_dtype == 0              ? launch_typed<bf16, float>(p, out, st, sp, smem, threads, grid, stage)
                                            : launch_typed<bf16, bf16>(p, out, st, sp, smem, threads, grid, stage);
+}
+
+// gather half of the split backward: grad_sampling_loc and grad_attn_weight (every element written, no memset needed)
+bool gather32_supported(const Problem &p)
+{
+    SlabParams sp;
+    size_t smem;
+    int threads, grid;
+    return make_tma(p, true, sp, smem, threads, grid, nullptr);
+}
+
+cudaError_t bwd_gather32(const Problem &p, const BackwardIO &io, cudaStream_t st)
+{
+    SlabParams sp;
+    size_t smem;
+    int threads, grid;
+    TmaMaps maps;
+    if ((long long)p.N * p.M * p.Lq == 0) return cudaSuccess;
+    if (!make_tma(p, true, sp, smem, threads, grid, &maps)) return cudaErrorInvalidValue;
+    return launch_tma<true>(p, nullptr, &io, st, sp, smem, threads, grid, maps);
 }
 
 }  // namespace msda

@@ -21,6 +21,7 @@
 // Every unit also prefetches the NEXT unit's locations, weights and value rows (and the next slab's grad_out rows) into L2.
 // A lane group is 8 lanes x 4 channels (one 128-byte row per LDS.128 phase: conflict-free); the three per-sample sums
 // are reduced over the 8 lanes with a transposed butterfly (4 shuffles instead of 9).
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -190,8 +191,9 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                 float2 xy = load2(locb + 2 * (q * qstride + p));
                 if (FUSED) {  // module prologue (ms_deform_attn.py:110-112): reference point + offset / (W_l, H_l)
                     const float2 rf = load2(ref + ((n * Lq + q) * sp.L + l) * 2);
-                    xy.x = __fadd_rn(rf.x, __fdiv_rn(xy.x, Wf));
-                    xy.y = __fadd_rn(rf.y, __fdiv_rn(xy.y, Hf));
+                    // (the same FMA with the host-rounded reciprocal as the forward: a sample lands in the same cell in both passes)
+                    xy.x = __fmaf_rn(xy.x, 1.0f / Wf, rf.x);
+                    xy.y = __fmaf_rn(xy.y, 1.0f / Hf, rf.y);
                 }
                 sx[r] = xy.x;
                 sy[r] = xy.y;
@@ -611,24 +613,11 @@ _Pragma("unroll") \
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-int sorted_split()
-{
-    static const int v = [] { const char *e = getenv("MSDA_SORTED_SPLIT"); const int x = e ? atoi(e) : 0; return x == 2 || x == 4 ? x : 8; }();
-    return v;
-}
+// (the A/B switches of round 1 -- lane splits 2 / 4, the cp.async grad_out ring, the deferred reduction, L2 prefetch -- all lost
+// against this configuration and are no longer instantiated: DESIGN.md section 5.6 keeps their measurements)
+constexpr int kSplit = 8, kModeLean = 16, kModeLeanFused = 20;
 
-int sorted_mode()  // bit 0: cp.async grad_out ring, bit 1: deferred reduction, bit 4 (16, the default): lean per-sample arithmetic
-{
-    static const int v = [] { const char *e = getenv("MSDA_SORTED_MODE"); return e ? atoi(e) & 19 : 16; }();
-    return v;
-}
-int sorted_prefetch()
-{
-    static const int v = [] { const char *e = getenv("MSDA_SORTED_PF"); const int x = e ? atoi(e) : 0; return x == 1 || x == 2 ? x : 0; }();  // 2: locations / weights only
-    return v;
-}
-
-bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
+bool make_params(const Problem &p, SortParams &sp, size_t &smem)
 {
     if (!((p.dtype == 0 || p.dtype == 1) && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
     if (p.Lq < 1 || p.Lq > 65535 || p.P > 16 || (long long)p.Lq * p.P > kMaxSamples) return false;
@@ -654,48 +643,45 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem, int &mode)
     if (sp.units >= (1LL << 30)) return false;  // 32-bit unit arithmetic in the kernel
     smem = (size_t)sp.vrows_max * 8 * 16 + ((size_t)p.Lq * p.P + 4) * 16 + (kMaxCells + 8 + 32) * sizeof(int) + kMaxCells * sizeof(int2);
     if (smem > (size_t)p.smem_optin) return false;
-    // three private 16-byte slots per chunk per thread for the cp.async grad_out pipeline, when they fit
-    const int split = sorted_split();
-    const size_t gring = (size_t)3 * (8 / split) * threads_for_split(split) * 16;
-    mode = sorted_mode();
-    if (smem + gring > (size_t)p.smem_optin) mode &= ~1;
-    if (mode & 1) smem += gring;
-    sp.prefetch = sorted_prefetch();
+    sp.prefetch = 0;
     sp.fused = p.ref != nullptr ? 1 : 0;
     if (sp.fused && p.loc_dtype != 0) return false;
-    if (sp.fused) mode &= 16;
     return true;
 }
 
-template <typename TV, typename TM>
-cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc, SortParams &sp, size_t smem, int mode, cudaStream_t st)
+template <auto Kern> cudaError_t ensure_smem_optin(const Problem &p)
 {
-    const int split = sorted_split();
-    auto pick = [&](auto pt, auto md) {
-        constexpr int PT = decltype(pt)::value, MD = decltype(md)::value;
-        return split == 2 ? bwd_sorted32_kernel<TV, TM, PT, 2, MD> : split == 4 ? bwd_sorted32_kernel<TV, TM, PT, 4, MD> : bwd_sorted32_kernel<TV, TM, PT, 8, MD>;
-    };
-    auto pick_mode = [&](auto pt) {
-        using std::integral_constant;
-        if (sp.fused) return (mode & 16) ? pick(pt, integral_constant<int, 20>()) : pick(pt, integral_constant<int, 4>());  // fused prologue
-        if (mode & 16) return (mode & 2) ? pick(pt, integral_constant<int, 18>()) : (mode & 1) ? pick(pt, integral_constant<int, 17>()) : pick(pt, integral_constant<int, 16>());
-        return mode == 3 ? pick(pt, integral_constant<int, 3>()) : mode == 2 ? pick(pt, integral_constant<int, 2>())
-             : mode == 1 ? pick(pt, integral_constant<int, 1>()) : pick(pt, integral_constant<int, 0>());
-    };
-    auto kern = p.P == 4 ? pick_mode(std::integral_constant<int, 4>()) : pick_mode(std::integral_constant<int, 0>());
-    const int kThreads = threads_for_split(split);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static std::atomic<unsigned long long> done{0};
+    const unsigned long long bit = 1ULL << (p.device & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_optin);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
+template <typename TV, typename TM>
+cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc, SortParams &sp, size_t smem, cudaStream_t st)
+{
     const int grid = (int)(sp.units < p.sm_count ? sp.units : p.sm_count);
     sp.base = (int)(sp.units / grid);
     sp.rem = (int)(sp.units - (long long)sp.base * grid);
     sp.parts = sp.rem > 0 ? grid / sp.rem : 1;
     if (sp.parts > 4) sp.parts = 4;
     if (sp.parts < 1) sp.parts = 1;
-    kern<<<grid, kThreads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (const TV *)io.grad_out, gv_acc,
-                                       (TM *)io.grad_loc, (TM *)io.grad_attn, (const TM *)p.ref, p.mask, sp);
-    count_launch();
-    return cudaGetLastError();
+    auto go = [&](auto kern_c) {
+        constexpr auto kern = decltype(kern_c)::value;
+        cudaError_t e = ensure_smem_optin<kern>(p);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, threads_for_split(kSplit), smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (const TV *)io.grad_out, gv_acc,
+                                                          (TM *)io.grad_loc, (TM *)io.grad_attn, (const TM *)p.ref, p.mask, sp);
+        count_launch();
+        return cudaGetLastError();
+    };
+    using std::integral_constant;
+#define MSDA_SORTED_KERN(PT, MD) integral_constant<decltype(&bwd_sorted32_kernel<TV, TM, PT, kSplit, MD>), &bwd_sorted32_kernel<TV, TM, PT, kSplit, MD>>()
+    if (sp.fused) return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeLeanFused)) : go(MSDA_SORTED_KERN(0, kModeLeanFused));
+    return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeLean)) : go(MSDA_SORTED_KERN(0, kModeLean));
+#undef MSDA_SORTED_KERN
 }
 
 }  // namespace
@@ -704,16 +690,14 @@ bool sorted32_supported(const Problem &p)
 {
     SortParams sp;
     size_t smem;
-    int mode;
-    return make_params(p, sp, smem, mode);
+    return make_params(p, sp, smem);
 }
 
 cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st)
 {
     SortParams sp;
     size_t smem;
-    int mode;
-    if (!make_params(p, sp, smem, mode)) return cudaErrorInvalidValue;
+    if (!make_params(p, sp, smem)) return cudaErrorInvalidValue;
     const long long n_val = (long long)p.N * p.S * p.M * p.D;
     float *acc = p.dtype == 0 ? (float *)io.grad_value : (float *)io.workspace;  // bf16: fp32 accumulation in the workspace
     if (n_val > 0) {
@@ -721,9 +705,9 @@ cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st
         if (e != cudaSuccess) return e;
     }
     if (sp.units == 0 || p.Lq == 0) return cudaSuccess;
-    cudaError_t e = p.dtype == 0      ? launch_sorted<float, float>(p, io, acc, sp, smem, mode, st)
-                    : p.loc_dtype == 0 ? launch_sorted<bf16, float>(p, io, acc, sp, smem, mode, st)
-                                       : launch_sorted<bf16, bf16>(p, io, acc, sp, smem, mode, st);
+    cudaError_t e = p.dtype == 0      ? launch_sorted<float, float>(p, io, acc, sp, smem, st)
+                    : p.loc_dtype == 0 ? launch_sorted<bf16, float>(p, io, acc, sp, smem, st)
+                                       : launch_sorted<bf16, bf16>(p, io, acc, sp, smem, st);
     if (e != cudaSuccess) return e;
     if (p.dtype == 1) return convert_f32_to_bf16(acc, io.grad_value, n_val, p.sm_count, st);
     return cudaSuccess;

@@ -87,8 +87,7 @@ int msda_backward(int dtype, int loc_dtype,
                   void *workspace, size_t workspace_bytes,
                   int device, void *stream);
 
-/* Scratch bytes msda_backward needs for this problem: the fp32 accumulator of grad_value for bf16 values, the sorted
- * sample lists of the experimental "pipe32" backward when that variant is forced (about 25 MB for the S4 shape), else 0. */
+/* Scratch bytes msda_backward needs for this problem: the fp32 accumulator of grad_value for bf16 values, else 0. */
 size_t msda_backward_workspace_bytes(int dtype, int loc_dtype, int N, int S, int M, int D, int L, int Lq, int P);
 
 /*

@@ -71,9 +71,10 @@ def test_argument_errors_need_no_gpu(lib):
 def test_workspace_query(lib):
     L = lib.load()
     assert L.msda_backward_workspace_bytes(0, 0, 40, 1029, 8, 32, 3, 1029, 4) == 0
-    # the experimental pipe32 backward (forced only) keeps two sorted sample lists per CTA: 192 CTAs x 2 x (Lq*P + 32) x 16 B
-    assert L.msda_select_variant(1, b"pipe32") == 0
-    assert L.msda_backward_workspace_bytes(0, 0, 40, 1029, 8, 32, 3, 1029, 4) == 192 * 2 * (1029 * 4 + 32) * 16
+    # no fp32 variant needs scratch, whichever is forced (the experimental pipe32 backward of round 1, which did, is gone)
+    assert L.msda_select_variant(1, b"split32") == 0
+    assert L.msda_backward_workspace_bytes(0, 0, 40, 1029, 8, 32, 3, 1029, 4) == 0
+    assert L.msda_select_variant(1, b"pipe32") != 0
     assert L.msda_select_variant(1, b"auto") == 0
     assert L.msda_backward_workspace_bytes(1, 0, 2, 10, 2, 32, 1, 5, 4) == 4 * 2 * 10 * 2 * 32
     assert L.msda_backward_workspace_bytes(1, 1, 0, 10, 2, 32, 1, 5, 4) == 0
