@@ -222,6 +222,20 @@ int msda_forward_backward_host(msda_host_pipeline *p, int dtype, int loc_dtype, 
     uint64_t up = 0, down = 0;
     const char *hv = (const char *)value, *hl = (const char *)sampling_loc, *ha = (const char *)attn_weight, *hg = (const char *)grad_output;
     char *ho = (char *)output, *hgv = (char *)grad_value, *hgl = (char *)grad_sampling_loc, *hga = (char *)grad_attn_weight;
+    // every early return below leaves copies of earlier chunks in flight between the caller's host buffers and the device: drain
+    // all pipeline streams before the caller gets control back (it may free those buffers as soon as it sees the error)
+    struct Drain {
+        msda_host_pipeline *p;
+        bool armed = true;
+        ~Drain()
+        {
+            if (!armed) return;
+            cudaStreamSynchronize(p->s_in);
+            cudaStreamSynchronize(p->s_in2);
+            cudaStreamSynchronize(p->s_run);
+            cudaStreamSynchronize(p->s_out);
+        }
+    } drain{p};
     int ci = 0;
     for (int lo = 0; lo < N; lo += chunk, ++ci) {
         const int n = (N - lo) < chunk ? (N - lo) : chunk;
@@ -282,6 +296,7 @@ int msda_forward_backward_host(msda_host_pipeline *p, int dtype, int loc_dtype, 
     cudaError_t e = cudaStreamSynchronize(p->s_out);  // every result is on the host when the call returns
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->s_run);
     if (e != cudaSuccess) return fail(p, (int)e, "pipeline execution", e);
+    drain.armed = false;
     if (trace) {
         for (size_t i = 0; i + 3 < tev.size() + 1 && i + 3 <= tev.size(); i += 4) {
             float a, b, c, d;

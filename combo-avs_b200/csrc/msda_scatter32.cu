@@ -36,6 +36,7 @@ struct ScatterParams {
     int qmax;                // queries per piece (<= Lq): bounds the sorted list
     long long total_q;       // N*M*L*Lq: the query sequence that is cut into gridDim.x equal ranges
     int fused;               // `loc` holds raw offsets: location = ref + offset * (1/W, 1/H)
+    int probe;               // profiling switches (MSDA_SCATTER_PROBE): 1 = sort phases only, 2 = no flush
 };
 
 struct f4p {
@@ -108,16 +109,19 @@ bwd_scatter32_kernel(const float *__restrict__ loc, const float *__restrict__ at
         const float *att = attn + meta0;
         const float *refb = FUSED ? ref + ((n * Lq + q_lo) * sp.L + l) * 2 : nullptr;
         const float rw = sp.rw[l], rh = sp.rh[l];
-        // cell of sample i of the piece (or -1 when it lies outside the map: cuh:352-356), optionally its fractions
-        auto locate = [&](int i, float &lh, float &lw, int &q) -> int {
-            q = P_T > 0 ? i / P_T : i / P;
-            const int p = i - q * P;
+        // raw location of sample i of the piece (the loads of a batch are issued together: one L2 round trip per batch, not per sample)
+        auto load_xy = [&](int i) -> float2 {
+            const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
             float2 xy = __ldg(reinterpret_cast<const float2 *>(locb + 2 * (q * qstride + p)));
             if (FUSED) {  // module prologue (ms_deform_attn.py:110-112), the same FMA as the forward and the gather kernel
                 const float2 rf = __ldg(reinterpret_cast<const float2 *>(refb + q * sp.L * 2));
                 xy.x = __fmaf_rn(xy.x, rw, rf.x);
                 xy.y = __fmaf_rn(xy.y, rh, rf.y);
             }
+            return xy;
+        };
+        // cell of a location (or -1 when it lies outside the map: cuh:352-356) and its fractions
+        auto locate = [&](float2 xy, float &lh, float &lw) -> int {
             const float h = __fmaf_rn(xy.y, Hf, -0.5f), w = __fmaf_rn(xy.x, Wf, -0.5f);
             if (!(h > -1.f && w > -1.f && h < Hf && w < Wf)) return -1;
             int y0, x0;
@@ -125,6 +129,7 @@ bwd_scatter32_kernel(const float *__restrict__ loc, const float *__restrict__ at
             lw = w - floor_magic(w, x0);
             return ((y0 + 1) << cs) + x0 + 1;
         };
+        constexpr int kBatch = 4;
         __syncthreads();  // the previous piece is completely finished with ent / cell_off
         for (int i = tid; i <= cells; i += kThreads) cell_off[i] = 0;
         for (int c = tid; c < cells; c += kThreads) {
@@ -135,11 +140,16 @@ bwd_scatter32_kernel(const float *__restrict__ loc, const float *__restrict__ at
         }
         __syncthreads();
         // ---- pass 1: histogram of the cells (shared-memory integer reductions, no return value) -----------------------------------
-        for (int i = tid; i < EP; i += kThreads) {
-            float lh, lw;
-            int q;
-            const int cell = locate(i, lh, lw, q);
-            if (cell >= 0) atomicAdd(&cell_off[cell], 1);
+        for (int i0 = tid; i0 < EP; i0 += kBatch * kThreads) {
+            float2 xy[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) xy[b] = i0 + b * kThreads < EP ? load_xy(i0 + b * kThreads) : make_float2(2.f, 2.f);
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                float lh, lw;
+                const int cell = locate(xy[b], lh, lw);
+                if (i0 + b * kThreads < EP && cell >= 0) atomicAdd(&cell_off[cell], 1);
+            }
         }
         __syncthreads();
         // ---- exclusive scan of the cell counters (<= kMaxCells cells, kCPT consecutive cells per thread) ---------------------------
@@ -179,26 +189,42 @@ bwd_scatter32_kernel(const float *__restrict__ loc, const float *__restrict__ at
             if (tid == kThreads - 1) {
                 const int tot = warp_tot[kThreads / 32 - 1];
                 cell_off[kMaxCells] = tot;  // number of in-range samples
-                // the grad_out prefetch runs up to three entries past a group's range without clamping: past the list's end it must
+                // the grad_out prefetch runs up to two entries past a group's range without clamping: past the list's end it must
                 // still find a valid query index (0)
                 for (int k = 0; k < 4; ++k) ent[tot + k] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         __syncthreads();
         // ---- pass 2: every in-range sample takes the next slot of its cell (the counters become per-cell cursors) -------------------
-        for (int i = tid; i < EP; i += kThreads) {
-            float lh = 0.f, lw = 0.f;
-            int q;
-            const int cell = locate(i, lh, lw, q);
-            if (cell >= 0) {
-                const int p = i - q * P;
-                const float a = __ldg(att + q * qstride + p);
-                const int slot = atomicAdd(&cell_off[cell], 1);
-                ent[slot] = make_float4(lh, lw, a, __int_as_float((cell << 16) | q));
+        for (int i0 = tid; i0 < EP; i0 += kBatch * kThreads) {
+            float2 xy[kBatch];
+            float av[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int i = i0 + b * kThreads;
+                xy[b] = make_float2(2.f, 2.f);
+                av[b] = 0.f;
+                if (i < EP) {
+                    const int q = P_T > 0 ? i / P_T : i / P, p = i - q * P;
+                    xy[b] = load_xy(i);
+                    av[b] = __ldg(att + q * qstride + p);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const int i = i0 + b * kThreads;
+                float lh = 0.f, lw = 0.f;
+                const int cell = locate(xy[b], lh, lw);
+                if (i < EP && cell >= 0) {
+                    const int q = P_T > 0 ? i / P_T : i / P;
+                    const int slot = atomicAdd(&cell_off[cell], 1);
+                    ent[slot] = make_float4(lh, lw, av[b], __int_as_float((cell << 16) | q));
+                }
             }
         }
         __syncthreads();  // sorted list complete
 
+        if (sp.probe & 1) continue;  // profiling: sort phases only
         // ---- walk the sorted list: every 8-lane group owns a contiguous range of entries ------------------------------------------
         const int E = cell_off[kMaxCells];
         const int e_lo = E * grp / kGroups, e_hi = E * (grp + 1) / kGroups;  // E <= 4608, grp < 48: fits 32 bits
@@ -214,6 +240,7 @@ bwd_scatter32_kernel(const float *__restrict__ loc, const float *__restrict__ at
         const float2 z2 = make_float2(0.f, 0.f);
         f4p a00 = {z2, z2}, a01 = a00, a10 = a00, a11 = a00;  // sums of att * (1, lw, lh, lh*lw) * g over the current cell's samples
         auto flush = [&]() {
+            if (sp.probe & 2) return;
             // (S0, S1, S2, S3) -> the four bilinear weights: (1-lh)(1-lw) = S0 - S1 - S2 + S3, (1-lh) lw = S1 - S3, lh (1-lw) = S2 - S3, lh lw = S3
             unsigned ci;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ci) : "r"(cinfo_s + cur * 4));
@@ -309,6 +336,8 @@ bool make_params(const Problem &p, ScatterParams &sp, size_t &smem)
     sp.qmax = (int)qmax;
     smem = (size_t)sp.qmax * p.P * 16 + fixed;
     sp.fused = p.ref != nullptr ? 1 : 0;
+    static const int probe = [] { const char *e = getenv("MSDA_SCATTER_PROBE"); return e ? atoi(e) : 0; }();
+    sp.probe = probe;
     return true;
 }
 

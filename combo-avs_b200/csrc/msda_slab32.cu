@@ -538,6 +538,7 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
         pin(off[k]);
     }
     pin(slab_s);
+    const unsigned pair_mask = 3u << (lane & 30);
     auto pass_range = [&](int u, int &nm, int &q0, int &cnt) {
         nm = u / sp.pps;
         q0 = (u - nm * sp.pps) * sp.qpp;
@@ -548,6 +549,19 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
         int nm, q0, cnt;
         pass_range(u_lo, nm, q0, cnt);
         stage_meta(meta0, loc, attn, sp, LP, nm, q0, cnt, fused ? refs0 : (float *)nullptr, ref, rpw);
+    }
+    float4 gnext[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) gnext[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (BWD) {
+        int nm, q0, cnt;
+        pass_range(u_lo, nm, q0, cnt);
+        const long long n = nm / sp.M;
+        const long long qm = (n * sp.Lq + q0 + ql) * sp.M + (nm - (int)n * sp.M);
+        if (ql < cnt) {
+#pragma unroll
+            for (int k = 0; k < CH; ++k) gnext[k] = ldg4(grad_out + qm * kD + (off[k] >> 2));
+        }
     }
     int it = 0, resident = nm_first;
     for (int u = u_lo; u < u_hi; ++u) {
@@ -576,10 +590,23 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
         float *row = meta + ql * 3 * LP;
         const float2 *loc2 = reinterpret_cast<const float2 *>(row);
         const float *att = row + 2 * LP;
-        float4 g[CH];
+        // BWD: the grad_output row of this (query, head) was loaded during the previous pass (a cold row costs an HBM round trip, which
+        // would otherwise sit at the head of every pass); now start the loads of the next pass's row
+        float4 g[CH], gn[CH];
         if (BWD) {
 #pragma unroll
-            for (int k = 0; k < CH; ++k) g[k] = live ? ldg4(grad_out + qm * kD + (off[k] >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < CH; ++k) g[k] = gnext[k];
+            if (u + 1 < u_hi) {
+                int nm2, q02, cnt2;
+                pass_range(u + 1, nm2, q02, cnt2);
+                const long long n2 = nm2 / sp.M;
+                const long long qm2 = (n2 * sp.Lq + q02 + ql) * sp.M + (nm2 - (int)n2 * sp.M);
+#pragma unroll
+                for (int k = 0; k < CH; ++k) gn[k] = ql < cnt2 ? ldg4(grad_out + qm2 * kD + (off[k] >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+#pragma unroll
+                for (int k = 0; k < CH; ++k) gn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         if (fused) {
             // Module prologue in place on the staged row (ops/modules/ms_deform_attn.py:102-116); the two lanes of the pair run one
@@ -735,9 +762,10 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
                             float ga = hh * (hw * s1 + lw * s2) + lh * (hw * s3 + lw * s4);
                             float gw = hh * (s2 - s1) + lh * (s4 - s3);
                             float gh = hw * (s3 - s1) + lw * (s4 - s2);
-                            ga += __shfl_xor_sync(0xffffffffu, ga, 1);
-                            gw += __shfl_xor_sync(0xffffffffu, gw, 1);
-                            gh += __shfl_xor_sync(0xffffffffu, gh, 1);
+                            // (only the lane's partner is named: lanes of rows past the end of the pass are not here)
+                            ga += __shfl_xor_sync(pair_mask, ga, 1);
+                            gw += __shfl_xor_sync(pair_mask, gw, 1);
+                            gh += __shfl_xor_sync(pair_mask, gh, 1);
                             // a sample outside the map has exactly zero gradients (cuh:352-356), whatever the clamped rows hold
                             if (part == 0) row[2 * LP + s] = ok ? ga : 0.f;
                             else reinterpret_cast<float2 *>(row)[s] = ok ? make_float2(sx * a_in * gw, sy * a_in * gh) : make_float2(0.f, 0.f);
@@ -772,6 +800,8 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
                 *reinterpret_cast<float4 *>(dst) = v;
             }
             __syncwarp();  // the rows are re-staged two passes from now by this warp's own cp.async
+#pragma unroll
+            for (int k = 0; k < CH; ++k) gnext[k] = gn[k];
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -123,11 +123,13 @@ class MSDeformAttnTransformerEncoderOnly(nn.Module):
         key = (shapes, str(device))
         hit = self._geometry.get(key)
         if hit is None:
-            spatial = torch.as_tensor(shapes, dtype=torch.long, device=device)
             starts = [0]
             for h, w in shapes[:-1]:
                 starts.append(starts[-1] + h * w)
-            hit = (spatial, torch.as_tensor(starts, dtype=torch.long, device=device))
+            # built outside inference mode even when the first forward runs inside it: a cached inference tensor could not be
+            # saved for backward by a later training step
+            with torch.inference_mode(False):
+                hit = (torch.as_tensor(shapes, dtype=torch.long, device=device), torch.as_tensor(starts, dtype=torch.long, device=device))
             self._geometry[key] = hit
         return hit
 

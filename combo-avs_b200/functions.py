@@ -24,10 +24,17 @@ _DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float64: _l
 _geometry_cache = {}
 
 
+def _version(t):
+    # inference tensors (created under torch.inference_mode()) have no version counter: in-place changes to them cannot be seen,
+    # so their host mirror is re-read on every call instead of cached (-1 never hits)
+    return -1 if t.is_inference() else t._version
+
+
 def _host_geometry(shapes, start):
     key = (id(shapes), id(start))
     hit = _geometry_cache.get(key)
-    if hit is not None and hit[0]() is shapes and hit[1]() is start and hit[2] == (shapes._version, start._version):
+    version = (_version(shapes), _version(start))
+    if hit is not None and hit[0]() is shapes and hit[1]() is start and hit[2] == version and -1 not in version:
         return hit[3]
     hs = shapes.detach().to("cpu", torch.int64).contiguous()
     hl = start.detach().to("cpu", torch.int64).contiguous()
@@ -37,7 +44,7 @@ def _host_geometry(shapes, start):
     def _drop(_ref, key=key):
         _geometry_cache.pop(key, None)
 
-    _geometry_cache[key] = (weakref.ref(shapes, _drop), weakref.ref(start, _drop), (shapes._version, start._version), geo)
+    _geometry_cache[key] = (weakref.ref(shapes, _drop), weakref.ref(start, _drop), version, geo)
     return geo
 
 
@@ -159,6 +166,9 @@ def fused_prologue_supported(value, spatial_shapes, level_start_index, reference
     N, S, M, D = value.shape
     L = spatial_shapes.shape[0]
     Lq, P = sampling_offsets.shape[1], sampling_offsets.shape[4]
+    # the reference's unfused arithmetic broadcasts reference points (e.g. [1, Lq, L, 2]); the kernels index them per frame
+    if tuple(reference_points.shape) != (N, Lq, L, 2):
+        return False
     hs, hl = _host_geometry(spatial_shapes, level_start_index)[:2]
     dev = value.device.index if value.device.index is not None else torch.cuda.current_device()
     return bool(_lib.load().msda_fused_supported(_lib.F32, N, S, M, D, L, Lq, P, hs, hl, dev))

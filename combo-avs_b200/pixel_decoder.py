@@ -119,8 +119,9 @@ class MSDeformAttnPixelDecoder(nn.Module):
         self.num_fpn_levels = int(math.log2(min(self.transformer_feature_strides)) - math.log2(common_stride))
         laterals, outputs = [], []
         for idx, channels in enumerate(self.feature_channels[: self.num_fpn_levels]):
-            lateral = ConvNormAct(channels, conv_dim, kernel_size=1, bias=norm in (None, ""), norm=_make_norm(norm, conv_dim))
-            output = ConvNormAct(conv_dim, conv_dim, kernel_size=3, stride=1, padding=1, bias=norm in (None, ""),
+            # msdeformattn.py:271: use_bias = norm == ""  (norm=None builds the convolutions without bias AND without norm)
+            lateral = ConvNormAct(channels, conv_dim, kernel_size=1, bias=norm == "", norm=_make_norm(norm, conv_dim))
+            output = ConvNormAct(conv_dim, conv_dim, kernel_size=3, stride=1, padding=1, bias=norm == "",
                                  norm=_make_norm(norm, conv_dim), activation=F.relu)
             _caffe2_xavier(lateral)
             _caffe2_xavier(output)
