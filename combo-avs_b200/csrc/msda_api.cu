@@ -22,9 +22,9 @@ thread_local char t_error[512] = "";
 std::atomic<const char *> g_last_variant[2] = {{"none"}, {"none"}};  // process-wide: backward runs on the autograd thread
 
 enum FwdVariant { kFwdAuto = 0, kFwdGeneric, kFwdWarp32, kFwdSlab32, kFwdCount };
-enum BwdVariant { kBwdAuto = 0, kBwdGeneric, kBwdWarp32, kBwdSorted32, kBwdSplit32, kBwdCount };
+enum BwdVariant { kBwdAuto = 0, kBwdGeneric, kBwdWarp32, kBwdSorted32, kBwdCount };
 const char *const kFwdNames[kFwdCount] = {"auto", "generic", "warp32", "slab32"};
-const char *const kBwdNames[kBwdCount] = {"auto", "generic", "warp32", "sorted32", "split32"};
+const char *const kBwdNames[kBwdCount] = {"auto", "generic", "warp32", "sorted32"};
 std::atomic<int> g_forced[2] = {{0}, {0}};
 
 int fail(int code, const char *fmt, ...)
@@ -121,20 +121,6 @@ int fill_problem(Problem &p, int dtype, int loc_dtype, const void *value, const 
     return MSDA_OK;
 }
 
-bool split32_supported(const Problem &p) { return gather32_supported(p) && scatter32_supported(p); }
-
-// grad_value is zeroed and accumulated by scatter32; grad_loc / grad_attn are written (every element) by gather32
-cudaError_t bwd_split32(const Problem &p, const BackwardIO &io, cudaStream_t st)
-{
-    // profiling switch: MSDA_SPLIT_PART=1 runs the gather half only, =2 the memset + scatter half only (results incomplete)
-    static const int part = [] { const char *e = getenv("MSDA_SPLIT_PART"); return e ? atoi(e) : 0; }();
-    const size_t n_val = (size_t)p.N * p.S * p.M * p.D;
-    cudaError_t e = (n_val > 0 && part != 1) ? cudaMemsetAsync(io.grad_value, 0, n_val * sizeof(float), st) : cudaSuccess;
-    if (e == cudaSuccess && part != 2) e = bwd_gather32(p, io, st);
-    if (e == cudaSuccess && part != 1) e = bwd_scatter32(p, io, st);
-    return e;
-}
-
 struct DeviceGuard {
     int prev = -1;
     bool switched = false;
@@ -169,7 +155,7 @@ uint64_t msda_launch_count(void) { return g_launches.load(std::memory_order_rela
 
 const char *msda_variant_names(int pass_)
 {
-    return pass_ == 0 ? "auto,generic,warp32,slab32" : "auto,generic,warp32,sorted32,split32";
+    return pass_ == 0 ? "auto,generic,warp32,slab32" : "auto,generic,warp32,sorted32";
 }
 
 const char *msda_last_variant(int pass_) { return (pass_ == 0 || pass_ == 1) ? g_last_variant[pass_].load() : "none"; }
@@ -264,14 +250,9 @@ int msda_backward(int dtype, int loc_dtype, const void *value, const int64_t *sp
 
     BackwardIO io{grad_output, grad_value, grad_sampling_loc, grad_attn_weight, workspace, workspace_bytes};
     int v = g_forced[1].load();
-    if (v == kBwdAuto) v = split32_supported(p) ? kBwdSplit32 : sorted32_supported(p) ? kBwdSorted32 : warp32_supported(p) ? kBwdWarp32 : kBwdGeneric;
+    if (v == kBwdAuto) v = sorted32_supported(p) ? kBwdSorted32 : warp32_supported(p) ? kBwdWarp32 : kBwdGeneric;
     if (S == 0) v = kBwdGeneric;
     switch (v) {
-    case kBwdSplit32:
-        if (!split32_supported(p))
-            return fail(MSDA_ERR_VARIANT, "backward variant split32 needs f32, D=32, L<=4, L*P %% 4 == 0, host geometry, (H+1)*(W+1) <= 1024 per level, a 16-byte aligned value pointer");
-        e = bwd_split32(p, io, st);
-        break;
     case kBwdSorted32:
         if (!sorted32_supported(p))
             return fail(MSDA_ERR_VARIANT, "backward variant sorted32 needs f32, D=32, host geometry, Lq*P <= 4608, (H+1)*(W+1) <= 1024 per level");

@@ -60,14 +60,6 @@ cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st);
 bool sorted32_supported(const Problem &p);
 cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st);
 
-// split32: the backward as two kernels on different pipes -- gather32 (grad_sampling_loc / grad_attn_weight by the forward's
-// shared-memory gather, TMA-staged slabs; msda_slab32.cu) and scatter32 (grad_value by sort-and-segment; msda_scatter32.cu,
-// accumulates into a zeroed grad_value)
-bool gather32_supported(const Problem &p);
-cudaError_t bwd_gather32(const Problem &p, const BackwardIO &io, cudaStream_t st);
-bool scatter32_supported(const Problem &p);
-cudaError_t bwd_scatter32(const Problem &p, const BackwardIO &io, cudaStream_t st);
-
 // zero the rows of grad[rows][row_elems] whose mask byte is set (masked_fill backward, ms_deform_attn.py:103-104)
 cudaError_t zero_masked_rows(float *grad, const unsigned char *mask, long long rows, int row_elems, int sm_count, cudaStream_t st);
 // softmax backward over the last L*P entries of every (frame, query, head) row, in place on grad (msda_generic.cu)

@@ -455,9 +455,7 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// TMA-pipelined slab kernel (float32 values and metadata): the default forward, and -- BWD -- the gather half of the split
-// backward (grad_sampling_loc / grad_attn_weight; ms_deform_im2col_cuda.cuh:92-164 without the grad_value scatter, which
-// msda_scatter32.cu does by sort-and-segment).
+// TMA-pipelined slab kernel (float32 values and metadata): the default forward.
 //
 // Same mapping, metadata staging and scheduling as fwd_slab32_kernel above.  What changes is how slabs move:
 //   * the last warp is a PRODUCER: one elected lane issues one cp.async.bulk.tensor per level (a (H+2) x (W+2) pixel box at
@@ -465,21 +463,19 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
 //   * full[l] / empty[l] mbarriers per level hand the level regions back and forth.  Consumers release level l of the resident
 //     slab as soon as their last pass is past it, so the next slab's small levels land while the 28x28 level is still being
 //     gathered, and its 28x28 level lands under the first pass's small levels -- the slab switch that the cp.async version
-//     serialises (a CTA barrier, 158 KB at the per-SM fill rate, another barrier per level) mostly disappears.
-// BWD: a lane pair holds the grad_output row of its (query, head) in registers (16 channels per lane), forms four dot products
-// with the neighbour rows per sample, combines them with the bilinear weights after the horizontal add, exchanges three partial
-// sums with its partner (one shuffle each) and writes the results IN PLACE over the staged locations / weights of its row; each
-// warp then streams its rows out with 16-byte stores (every 32-byte sector of grad_loc / grad_attn is written exactly once).
+//     serialises (a CTA barrier, 158 KB at the per-SM fill rate, another barrier per level) mostly disappears: 82.3 -> 73.9 us.
+// (Round 2 also built the backward's grad_sampling_loc / grad_attn_weight as a second mode of this kernel -- a by-query gather next
+// to a grad_value-only sort-and-segment kernel.  Parity-green, but 110 + 132 us against 206 us for msda_sorted32.cu, which does
+// both in one walk with fewer instructions in total: removed again, measurements in profiles/r04_split_backward_experiments.txt.)
 struct alignas(64) TmaMaps {
     CUtensorMap level[4];
 };
 constexpr int kTmaMaxLevels = 4;
-constexpr int kFwdTmaThreads = 512, kBwdTmaThreads = 416;  // including the producer warp
+constexpr int kFwdTmaThreads = 512;  // including the producer warp
 
-template <int P_T, bool BWD>
-__global__ void __launch_bounds__(BWD ? kBwdTmaThreads : kFwdTmaThreads, 1)
+template <int P_T>
+__global__ void __launch_bounds__(kFwdTmaThreads, 1)
 slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn, float *__restrict__ out,
-                  const float *__restrict__ grad_out, float *__restrict__ grad_loc, float *__restrict__ grad_attn,
                   const float *__restrict__ ref, float *__restrict__ attn_out, const unsigned char *__restrict__ mask,
                   const __grid_constant__ SlabParams sp, const __grid_constant__ TmaMaps maps)
 {
@@ -538,7 +534,6 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
         pin(off[k]);
     }
     pin(slab_s);
-    const unsigned pair_mask = 3u << (lane & 30);
     auto pass_range = [&](int u, int &nm, int &q0, int &cnt) {
         nm = u / sp.pps;
         q0 = (u - nm * sp.pps) * sp.qpp;
@@ -549,19 +544,6 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
         int nm, q0, cnt;
         pass_range(u_lo, nm, q0, cnt);
         stage_meta(meta0, loc, attn, sp, LP, nm, q0, cnt, fused ? refs0 : (float *)nullptr, ref, rpw);
-    }
-    float4 gnext[CH];
-#pragma unroll
-    for (int k = 0; k < CH; ++k) gnext[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (BWD) {
-        int nm, q0, cnt;
-        pass_range(u_lo, nm, q0, cnt);
-        const long long n = nm / sp.M;
-        const long long qm = (n * sp.Lq + q0 + ql) * sp.M + (nm - (int)n * sp.M);
-        if (ql < cnt) {
-#pragma unroll
-            for (int k = 0; k < CH; ++k) gnext[k] = ldg4(grad_out + qm * kD + (off[k] >> 2));
-        }
     }
     int it = 0, resident = nm_first;
     for (int u = u_lo; u < u_hi; ++u) {
@@ -590,33 +572,14 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
         float *row = meta + ql * 3 * LP;
         const float2 *loc2 = reinterpret_cast<const float2 *>(row);
         const float *att = row + 2 * LP;
-        // BWD: the grad_output row of this (query, head) was loaded during the previous pass (a cold row costs an HBM round trip, which
-        // would otherwise sit at the head of every pass); now start the loads of the next pass's row
-        float4 g[CH], gn[CH];
-        if (BWD) {
-#pragma unroll
-            for (int k = 0; k < CH; ++k) g[k] = gnext[k];
-            if (u + 1 < u_hi) {
-                int nm2, q02, cnt2;
-                pass_range(u + 1, nm2, q02, cnt2);
-                const long long n2 = nm2 / sp.M;
-                const long long qm2 = (n2 * sp.Lq + q02 + ql) * sp.M + (nm2 - (int)n2 * sp.M);
-#pragma unroll
-                for (int k = 0; k < CH; ++k) gn[k] = ql < cnt2 ? ldg4(grad_out + qm2 * kD + (off[k] >> 2)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-#pragma unroll
-                for (int k = 0; k < CH; ++k) gn[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
         if (fused) {
             // Module prologue in place on the staged row (ops/modules/ms_deform_attn.py:102-116); the two lanes of the pair run one
-            // instruction stream on the two halves of the row.  Forward: softmax over the L*P logits (max and sum exchanged with one
-            // shuffle each; ex2-based exp, one reciprocal) and location = reference point + offset * (1/W_l, 1/H_l) (one FMA).
-            // Backward: the weights arrive softmaxed (saved by the forward); only the locations are rebuilt, with the same FMA.
+            // instruction stream on the two halves of the row: softmax over the L*P logits (max and sum exchanged with one shuffle
+            // each; ex2-based exp, one reciprocal) and location = reference point + offset * (1/W_l, 1/H_l) (one FMA).
             const int hl = LP >> 1;  // LP % 4 == 0
             float *lg = row + 2 * LP + part * hl;
             const float *rf = refs0 + ((u - u_lo) & 1) * ref_stride + ql * sp.L * 2;
-            if (!BWD && LP == 12 && P == 4) {
+            if (LP == 12 && P == 4) {
                 // the production shape (3 levels x 4 points): the lane's half row lives in registers, vector loads / stores only
                 float2 g0 = make_float2(0.f, 0.f), g1 = g0, g2 = g0;
                 float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0, o2 = o0;
@@ -649,27 +612,25 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
                     xy4[0] = o0; xy4[1] = o1; xy4[2] = o2;
                 }
             } else {
-                if (!BWD) {
-                    float mx = -3.0e38f;
-                    if (live)
-                        for (int i = 0; i < hl; ++i) mx = fmaxf(mx, lg[i]);
-                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                    float sum = 0.f;
-                    if (live)
-                        for (int i = 0; i < hl; ++i) {
-                            const float e = __expf(lg[i] - mx);
-                            lg[i] = e;
-                            sum += e;
-                        }
-                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                    if (live) {
-                        const float inv = __frcp_rn(sum);
-                        float2 *ao = reinterpret_cast<float2 *>(attn_out + qm * LP + part * hl);
-                        for (int i = 0; i < hl; i += 2) {
-                            const float2 a2 = make_float2(lg[i] * inv, lg[i + 1] * inv);
-                            *reinterpret_cast<float2 *>(lg + i) = a2;
-                            ao[i >> 1] = a2;
-                        }
+                float mx = -3.0e38f;
+                if (live)
+                    for (int i = 0; i < hl; ++i) mx = fmaxf(mx, lg[i]);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                float sum = 0.f;
+                if (live)
+                    for (int i = 0; i < hl; ++i) {
+                        const float e = __expf(lg[i] - mx);
+                        lg[i] = e;
+                        sum += e;
+                    }
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                if (live) {
+                    const float inv = __frcp_rn(sum);
+                    float2 *ao = reinterpret_cast<float2 *>(attn_out + qm * LP + part * hl);
+                    for (int i = 0; i < hl; i += 2) {
+                        const float2 a2 = make_float2(lg[i] * inv, lg[i + 1] * inv);
+                        *reinterpret_cast<float2 *>(lg + i) = a2;
+                        ao[i >> 1] = a2;
                     }
                 }
                 if (live) {
@@ -713,7 +674,6 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
                 const int pitch = sp.W[l] + 2;
                 const unsigned lvl_s = slab_s + (unsigned)(sp.prow0[l] + pitch + 1) * kRowBytes;  // address of pixel (0,0)
                 const unsigned pitch_b = (unsigned)pitch * kRowBytes;
-                const float sx = fused ? 1.f : Wf, sy = fused ? 1.f : Hf;  // d(loc)/d(offset) = 1/(W, H) cancels the (W, H) of cuh:126-127
 #pragma unroll
                 for (int pp = 0; pp < (P_T > 0 ? P_T : 1); ++pp) {
                     for (int p = (P_T > 0 ? pp : 0); p < (P_T > 0 ? pp + 1 : P); ++p) {
@@ -730,45 +690,18 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
                         const float lh = hc - fh, lw = wc - fw;
                         const unsigned r00 = lvl_s + (unsigned)(y0 * pitch + x0) * kRowBytes;
                         const unsigned r10 = r00 + pitch_b;
-                        if (!BWD) {
-                            const float a = ok ? a_in : 0.f;
-                            const float ahh = a * (1.f - lh), alh = a * lh, hw = 1.f - lw;
-                            const float w1s = ahh * hw, w2s = ahh * lw, w3s = alh * hw, w4s = alh * lw;
-                            const float2 w1 = make_float2(w1s, w1s), w2 = make_float2(w2s, w2s), w3 = make_float2(w3s, w3s), w4 = make_float2(w4s, w4s);
+                        const float a = ok ? a_in : 0.f;
+                        const float ahh = a * (1.f - lh), alh = a * lh, hw = 1.f - lw;
+                        const float w1s = ahh * hw, w2s = ahh * lw, w3s = alh * hw, w4s = alh * lw;
+                        const float2 w1 = make_float2(w1s, w1s), w2 = make_float2(w2s, w2s), w3 = make_float2(w3s, w3s), w4 = make_float2(w4s, w4s);
 #pragma unroll
-                            for (int k = 0; k < CH; ++k) {
-                                const float4 v1 = lds4(r00 + off[k]), v2 = lds4(r00 + off[k] + kRowBytes);
-                                const float4 v3 = lds4(r10 + off[k]), v4 = lds4(r10 + off[k] + kRowBytes);
-                                acc[k].lo = __ffma2_rn(w1, make_float2(v1.x, v1.y), __ffma2_rn(w2, make_float2(v2.x, v2.y),
-                                            __ffma2_rn(w3, make_float2(v3.x, v3.y), __ffma2_rn(w4, make_float2(v4.x, v4.y), acc[k].lo))));
-                                acc[k].hi = __ffma2_rn(w1, make_float2(v1.z, v1.w), __ffma2_rn(w2, make_float2(v2.z, v2.w),
-                                            __ffma2_rn(w3, make_float2(v3.z, v3.w), __ffma2_rn(w4, make_float2(v4.z, v4.w), acc[k].hi))));
-                            }
-                        } else {
-                            float2 d1 = make_float2(0.f, 0.f), d2 = d1, d3 = d1, d4 = d1;  // lane-partial dot products of g with the four neighbours
-#pragma unroll
-                            for (int k = 0; k < CH; ++k) {
-                                const float4 v1 = lds4(r00 + off[k]), v2 = lds4(r00 + off[k] + kRowBytes);
-                                const float4 v3 = lds4(r10 + off[k]), v4 = lds4(r10 + off[k] + kRowBytes);
-                                const float2 glo = make_float2(g[k].x, g[k].y), ghi = make_float2(g[k].z, g[k].w);
-                                d1 = __ffma2_rn(ghi, make_float2(v1.z, v1.w), __ffma2_rn(glo, make_float2(v1.x, v1.y), d1));
-                                d2 = __ffma2_rn(ghi, make_float2(v2.z, v2.w), __ffma2_rn(glo, make_float2(v2.x, v2.y), d2));
-                                d3 = __ffma2_rn(ghi, make_float2(v3.z, v3.w), __ffma2_rn(glo, make_float2(v3.x, v3.y), d3));
-                                d4 = __ffma2_rn(ghi, make_float2(v4.z, v4.w), __ffma2_rn(glo, make_float2(v4.x, v4.y), d4));
-                            }
-                            const float s1 = d1.x + d1.y, s2 = d2.x + d2.y, s3 = d3.x + d3.y, s4 = d4.x + d4.y;
-                            const float hh = 1.f - lh, hw = 1.f - lw;
-                            // cuh:104-160: val = sum_i w_i v_i; grad_w = hh (v2 - v1) + lh (v4 - v3); grad_h = hw (v3 - v1) + lw (v4 - v2)
-                            float ga = hh * (hw * s1 + lw * s2) + lh * (hw * s3 + lw * s4);
-                            float gw = hh * (s2 - s1) + lh * (s4 - s3);
-                            float gh = hw * (s3 - s1) + lw * (s4 - s2);
-                            // (only the lane's partner is named: lanes of rows past the end of the pass are not here)
-                            ga += __shfl_xor_sync(pair_mask, ga, 1);
-                            gw += __shfl_xor_sync(pair_mask, gw, 1);
-                            gh += __shfl_xor_sync(pair_mask, gh, 1);
-                            // a sample outside the map has exactly zero gradients (cuh:352-356), whatever the clamped rows hold
-                            if (part == 0) row[2 * LP + s] = ok ? ga : 0.f;
-                            else reinterpret_cast<float2 *>(row)[s] = ok ? make_float2(sx * a_in * gw, sy * a_in * gh) : make_float2(0.f, 0.f);
+                        for (int k = 0; k < CH; ++k) {
+                            const float4 v1 = lds4(r00 + off[k]), v2 = lds4(r00 + off[k] + kRowBytes);
+                            const float4 v3 = lds4(r10 + off[k]), v4 = lds4(r10 + off[k] + kRowBytes);
+                            acc[k].lo = __ffma2_rn(w1, make_float2(v1.x, v1.y), __ffma2_rn(w2, make_float2(v2.x, v2.y),
+                                        __ffma2_rn(w3, make_float2(v3.x, v3.y), __ffma2_rn(w4, make_float2(v4.x, v4.y), acc[k].lo))));
+                            acc[k].hi = __ffma2_rn(w1, make_float2(v1.z, v1.w), __ffma2_rn(w2, make_float2(v2.z, v2.w),
+                                        __ffma2_rn(w3, make_float2(v3.z, v3.w), __ffma2_rn(w4, make_float2(v4.z, v4.w), acc[k].hi))));
                         }
                     }
                 }
@@ -778,30 +711,10 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
                 if (lane == 0) mbar_arrive(bars + 8 * (kTmaMaxLevels + l));
             }
         }
-        if (!BWD) {
-            if (live) {
-                float *o = out + qm * kD;
+        if (live) {
+            float *o = out + qm * kD;
 #pragma unroll
-                for (int k = 0; k < CH; ++k) store4(o + (off[k] >> 2), make_float4(acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y));
-            }
-        } else {
-            // stream this warp's rows out: per row 2*LP grad_loc floats, then LP grad_attn floats, as 16-byte pieces
-            __syncwarp();
-            const int r0 = wid * rpw, nrows = min(max(cnt - r0, 0), rpw);
-            const int pieces = (3 * LP) >> 2, loc_pieces = LP >> 1;
-            const long long qm0 = ((long long)(nm / sp.M) * sp.Lq + q0 + r0) * sp.M + m;
-            float *lbase = grad_loc + qm0 * (2 * LP), *abase = grad_attn + qm0 * LP;
-            const int lstride = sp.M * 2 * LP, astride = sp.M * LP;
-            const float *mrow = meta + r0 * (3 * LP);
-            for (int i = lane; i < nrows * pieces; i += 32) {
-                const int rq = (int)__umulhi((unsigned)i, sp.precip), pc = i - rq * pieces;
-                const float4 v = *reinterpret_cast<const float4 *>(mrow + rq * (3 * LP) + pc * 4);
-                float *dst = pc < loc_pieces ? lbase + rq * lstride + pc * 4 : abase + rq * astride + (pc - loc_pieces) * 4;
-                *reinterpret_cast<float4 *>(dst) = v;
-            }
-            __syncwarp();  // the rows are re-staged two passes from now by this warp's own cp.async
-#pragma unroll
-            for (int k = 0; k < CH; ++k) gnext[k] = gn[k];
+            for (int k = 0; k < CH; ++k) store4(o + (off[k] >> 2), make_float4(acc[k].lo.x, acc[k].lo.y, acc[k].hi.x, acc[k].hi.y));
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -912,13 +825,13 @@ cudaError_t launch_typed(const Problem &p, void *out, cudaStream_t st, const Sla
 
 // The TMA kernel applies to float32 values + float32 metadata, L <= 4, L*P % 4 == 0, levels that fit a 256 x 256 box and a
 // 16-byte aligned value pointer; everything else keeps the cp.async kernel (forward) / the sorted backward.
-bool make_tma(const Problem &p, bool bwd, SlabParams &sp, size_t &smem, int &threads, int &grid, TmaMaps *maps)
+bool make_tma(const Problem &p, SlabParams &sp, size_t &smem, int &threads, int &grid, TmaMaps *maps)
 {
     static const bool off = [] { const char *e = getenv("MSDA_SLAB_TMA"); return e && atoi(e) == 0; }();  // A/B switch
     if (off || p.dtype != 0 || p.loc_dtype != 0 || p.L > kTmaMaxLevels) return false;
     bool stage;
-    if (!make_params(p, sp, smem, threads, grid, stage, (bwd ? kBwdTmaThreads : kFwdTmaThreads) - 32) || !stage) return false;
-    if (!bwd && p.ref != nullptr && p.attn_out == nullptr) return false;
+    if (!make_params(p, sp, smem, threads, grid, stage, kFwdTmaThreads - 32) || !stage) return false;
+    if (p.ref != nullptr && p.attn_out == nullptr) return false;
     smem += 2 * kTmaMaxLevels * 8;  // full[l], empty[l]
     if (smem > (size_t)p.smem_optin) return false;
     threads += 32;  // the producer warp
@@ -932,23 +845,19 @@ bool make_tma(const Problem &p, bool bwd, SlabParams &sp, size_t &smem, int &thr
     return true;
 }
 
-template <bool BWD>
-cudaError_t launch_tma(const Problem &p, void *out, const BackwardIO *io, cudaStream_t st, const SlabParams &sp, size_t smem, int threads,
-                       int grid, const TmaMaps &maps)
+cudaError_t launch_tma(const Problem &p, void *out, cudaStream_t st, const SlabParams &sp, size_t smem, int threads, int grid, const TmaMaps &maps)
 {
     auto go = [&](auto kern_c) {
         constexpr auto kern = decltype(kern_c)::value;
         cudaError_t e = ensure_smem_optin<kern>(p);
         if (e != cudaSuccess) return e;
-        kern<<<grid, threads, smem, st>>>((const float *)p.loc, (const float *)p.attn, (float *)out, io ? (const float *)io->grad_out : nullptr,
-                                          io ? (float *)io->grad_loc : nullptr, io ? (float *)io->grad_attn : nullptr, (const float *)p.ref,
-                                          (float *)p.attn_out, p.mask, sp, maps);
+        kern<<<grid, threads, smem, st>>>((const float *)p.loc, (const float *)p.attn, (float *)out, (const float *)p.ref, (float *)p.attn_out, p.mask, sp, maps);
         count_launch();
         return cudaGetLastError();
     };
     using std::integral_constant;
-    if (p.P == 4) return go(integral_constant<decltype(&slab32_tma_kernel<4, BWD>), &slab32_tma_kernel<4, BWD>>());
-    return go(integral_constant<decltype(&slab32_tma_kernel<0, BWD>), &slab32_tma_kernel<0, BWD>>());
+    if (p.P == 4) return go(integral_constant<decltype(&slab32_tma_kernel<4>), &slab32_tma_kernel<4>>());
+    return go(integral_constant<decltype(&slab32_tma_kernel<0>), &slab32_tma_kernel<0>>());
 }
 
 }  // namespace
@@ -972,33 +881,13 @@ cudaError_t fwd_slab32(const Problem &p, void *out, cudaStream_t st)
     if ((long long)p.N * p.M * p.Lq == 0) return cudaSuccess;
     {
         TmaMaps maps;
-        if (make_tma(p, false, sp, smem, threads, grid, &maps)) return launch_tma<false>(p, out, nullptr, st, sp, smem, threads, grid, maps);
+        if (make_tma(p, sp, smem, threads, grid, &maps)) return launch_tma(p, out, st, sp, smem, threads, grid, maps);
     }
     if (!make_params(p, sp, smem, threads, grid, stage, 512)) return cudaErrorInvalidValue;
     if (p.ref != nullptr && p.attn_out == nullptr) return cudaErrorInvalidValue;
     return p.dtype == 0                    ? launch_typed<float, float>(p, out, st, sp, smem, threads, grid, stage)
            : p.loc_dtype == 0              ? launch_typed<bf16, float>(p, out, st, sp, smem, threads, grid, stage)
                                            : launch_typed<bf16, bf16>(p, out, st, sp, smem, threads, grid, stage);
-}
-
-// gather half of the split backward: grad_sampling_loc and grad_attn_weight (every element written, no memset needed)
-bool gather32_supported(const Problem &p)
-{
-    SlabParams sp;
-    size_t smem;
-    int threads, grid;
-    return make_tma(p, true, sp, smem, threads, grid, nullptr);
-}
-
-cudaError_t bwd_gather32(const Problem &p, const BackwardIO &io, cudaStream_t st)
-{
-    SlabParams sp;
-    size_t smem;
-    int threads, grid;
-    TmaMaps maps;
-    if ((long long)p.N * p.M * p.Lq == 0) return cudaSuccess;
-    if (!make_tma(p, true, sp, smem, threads, grid, &maps)) return cudaErrorInvalidValue;
-    return launch_tma<true>(p, nullptr, &io, st, sp, smem, threads, grid, maps);
 }
 
 }  // namespace msda

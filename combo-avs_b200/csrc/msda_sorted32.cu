@@ -46,6 +46,7 @@ struct SortParams {
     int base;                // whole units per CTA
     int rem;                 // leftover units (units - base*grid), each cut into `parts` pieces: one piece per CTA
     int parts;
+    int zero_frames;         // whole units of frames < zero_frames zero their own grad_value slab (the host zeroes the other frames)
     int prefetch;            // L2-prefetch the next unit's inputs during the walk
     int fused;               // `loc` holds raw offsets: location = ref + offset / (W, H); grad_loc is then d/d(offset)
 };
@@ -87,9 +88,7 @@ __device__ __forceinline__ float4 lds4(unsigned addr)
     return v;
 }
 
-// MODE bit 5 (32): no value slab in shared memory -- a cell's four value rows come through L1 when the walk enters the cell -- so the
-// CTA needs 78 KB instead of 193 KB and TWO CTAs of 384 threads share an SM: the sort phases of one run under the walk of the other
-__host__ __device__ constexpr int threads_for_split(int split, int mode = 0) { return (mode & 32) ? 384 : split == 8 ? 768 : split == 4 ? 512 : 384; }
+__host__ __device__ constexpr int threads_for_split(int split) { return split == 8 ? 768 : split == 4 ? 512 : 384; }
 
 using bf16 = __nv_bfloat16;
 __device__ __forceinline__ float4 load4(const float *p) { return ldg4(p); }
@@ -113,20 +112,19 @@ __device__ __forceinline__ void store2(bf16 *p, float a, float b) { *reinterpret
 // TV: value / grad_out element type (float or bf16; grad_value always accumulates in fp32: for bf16 into a workspace that a
 // second kernel narrows).  TM: element type of sampling locations, attention weights and their gradients.
 template <typename TV, typename TM, int P_T, int SPLIT, int MODE>
-__global__ void __launch_bounds__(threads_for_split(SPLIT, MODE), (MODE & 32) ? 2 : 1)
+__global__ void __launch_bounds__(threads_for_split(SPLIT), 1)
 bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, const TM *__restrict__ attn,
                     const TV *__restrict__ grad_out, float *__restrict__ grad_value, TM *__restrict__ grad_loc,
                     TM *__restrict__ grad_attn, const TM *__restrict__ ref, const unsigned char *__restrict__ mask,
                     const __grid_constant__ SortParams sp)
 {
-    constexpr int kThreads = threads_for_split(SPLIT, MODE), CH = 8 / SPLIT;
-    constexpr bool NOSLAB = (MODE & 32) != 0;
+    constexpr int kThreads = threads_for_split(SPLIT), CH = 8 / SPLIT;
     constexpr int kGroups = kThreads / SPLIT, kRounds = (kMaxSamples + kThreads - 1) / kThreads;
     constexpr int kCPT = (kMaxCells + kThreads - 1) / kThreads;  // cells scanned per thread
     extern __shared__ float4 smem4[];
     const int Lq = sp.Lq, P = P_T > 0 ? P_T : sp.P, EP = Lq * P, LP = sp.L * P;
     float4 *V4 = smem4;                                   // zero-padded value slab of the current level: (H+2) x (W+2) rows
-    float4 *ent = smem4 + (NOSLAB ? 0 : (size_t)sp.vrows_max * 8);  // sorted samples: {lh, lw, attn, cell<<20 | p<<16 | q}
+    float4 *ent = smem4 + (size_t)sp.vrows_max * 8;       // sorted samples: {lh, lw, attn, cell<<20 | p<<16 | q}
     int *cell_off = reinterpret_cast<int *>(ent + EP + 4);  // (four spare entries, see the prefetch) kMaxCells + 1 counters -> exclusive offsets
     int *warp_tot = cell_off + kMaxCells + 8;
     constexpr bool GRING = (MODE & 1) != 0, DEFER = (MODE & 2) != 0, FUSED = (MODE & 4) != 0;
@@ -205,8 +203,7 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         }
         // (the slab copy and the zero fills below overlap the latency of the loads just issued)
         // value level slab -> shared memory (interior by cp.async, the one-pixel border zeroed by hand)
-        if (NOSLAB) {
-        } else if (sizeof(TV) == 4) {
+        if (sizeof(TV) == 4) {
             for (int i = tid; i < H * W * 8; i += kThreads) {
                 const int pxl = i >> 3, c = i & 7;
                 const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
@@ -220,7 +217,15 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (!NOSLAB) {
+        // A unit this CTA owns alone zeroes its own slab of grad_value here, right before it accumulates into it: the lines are
+        // still in L2 when the reductions arrive, and no 42 MB memset runs ahead of the kernel.  (The few leftover units that
+        // several CTAs share lie in the frames >= zero_frames, which the host zeroes with a small memset.)
+        if (!piece && n < sp.zero_frames) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float *gvl = grad_value + lvl_row;
+            for (int i = tid; i < H * W * 8; i += kThreads) *reinterpret_cast<float4 *>(gvl + (i >> 3) * pix + (i & 7) * 4) = z;
+        }
+        {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int i = tid; i < Wp * 8; i += kThreads) {  // top and bottom padded rows
                 V4[i] = z;
@@ -485,18 +490,8 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                     const unsigned vr = V_s + (unsigned)(ci.x & ~127); \
 _Pragma("unroll") \
                     for (int k = 0; k < CH; ++k) { \
-                        f4p t00, t01, t10, t11; \
-                        if (NOSLAB) { /* neighbours outside the map read as zero (cuh:58-82); value and grad_value share their layout */ \
-                            const TV *vk = vbase + ci.y + chf[k]; \
-                            const float4 z4v = make_float4(0.f, 0.f, 0.f, 0.f); \
-                            t00 = pk((inmask & 1) ? load4(vk) : z4v); \
-                            t01 = pk((inmask & 2) ? load4(vk + o01) : z4v); \
-                            t10 = pk((inmask & 4) ? load4(vk + o10) : z4v); \
-                            t11 = pk((inmask & 8) ? load4(vk + o11) : z4v); \
-                        } else { \
-                            const unsigned a = vr + chf[k] * 4; \
-                            t00 = pk(lds4(a)); t01 = pk(lds4(a + kD * 4)); t10 = pk(lds4(a + Wpb)); t11 = pk(lds4(a + Wpb + kD * 4)); \
-                        } \
+                        const unsigned a = vr + chf[k] * 4; \
+                        const f4p t00 = pk(lds4(a)), t01 = pk(lds4(a + kD * 4)), t10 = pk(lds4(a + Wpb)), t11 = pk(lds4(a + Wpb + kD * 4)); \
                         v00[k] = t00; \
                         dW[k] = psub(t01, t00); \
                         dH[k] = psub(t10, t00); \
@@ -629,14 +624,9 @@ _Pragma("unroll") \
 
 // (the A/B switches of round 1 -- lane splits 2 / 4, the cp.async grad_out ring, the deferred reduction, L2 prefetch -- all lost
 // against this configuration and are no longer instantiated: DESIGN.md section 5.6 keeps their measurements)
-constexpr int kSplit = 8, kModeLean = 16, kModeLeanFused = 20, kModeNoSlab = 32;
-bool sorted_noslab()
-{
-    static const bool v = [] { const char *e = getenv("MSDA_SORTED_NOSLAB"); return e ? atoi(e) != 0 : true; }();  // A/B switch
-    return v;
-}
+constexpr int kSplit = 8, kModeLean = 16, kModeLeanFused = 20;
 
-bool make_params(const Problem &p, SortParams &sp, size_t &smem, bool &noslab)
+bool make_params(const Problem &p, SortParams &sp, size_t &smem)
 {
     if (!((p.dtype == 0 || p.dtype == 1) && p.D == kD && p.have_host && p.L <= kMaxLevels)) return false;
     if (p.Lq < 1 || p.Lq > 65535 || p.P > 16 || (long long)p.Lq * p.P > kMaxSamples) return false;
@@ -660,9 +650,7 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem, bool &noslab)
     }
     sp.units = (long long)p.N * p.M * p.L;
     if (sp.units >= (1LL << 30)) return false;  // 32-bit unit arithmetic in the kernel
-    // the slab-less form takes float32 values without a padding mask (a masked pixel would need a per-row predicate)
-    noslab = sorted_noslab() && p.dtype == 0 && p.mask == nullptr;
-    smem = (noslab ? 0 : (size_t)sp.vrows_max * 8 * 16) + ((size_t)p.Lq * p.P + 4) * 16 + (kMaxCells + 8 + 32) * sizeof(int) + kMaxCells * sizeof(int2);
+    smem = (size_t)sp.vrows_max * 8 * 16 + ((size_t)p.Lq * p.P + 4) * 16 + (kMaxCells + 8 + 32) * sizeof(int) + kMaxCells * sizeof(int2);
     if (smem > (size_t)p.smem_optin) return false;
     sp.prefetch = 0;
     sp.fused = p.ref != nullptr ? 1 : 0;
@@ -680,34 +668,38 @@ template <auto Kern> cudaError_t ensure_smem_optin(const Problem &p)
     return e;
 }
 
-template <typename TV, typename TM>
-cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc, SortParams &sp, size_t smem, bool noslab, cudaStream_t st)
+// schedule: `grid` persistent CTAs take `base` whole units each; the `rem` leftover units are cut into `parts` pieces, one per CTA
+void plan_units(const Problem &p, SortParams &sp, int &grid)
 {
-    const int slots = p.sm_count * (noslab ? 2 : 1);
-    const int grid = (int)(sp.units < slots ? sp.units : slots);
+    grid = (int)(sp.units < p.sm_count ? sp.units : p.sm_count);
     sp.base = (int)(sp.units / grid);
     sp.rem = (int)(sp.units - (long long)sp.base * grid);
     sp.parts = sp.rem > 0 ? grid / sp.rem : 1;
     if (sp.parts > 4) sp.parts = 4;
     if (sp.parts < 1) sp.parts = 1;
+    // whole units zero their own grad_value slab in the kernel; the leftover units start at unit grid*base, i.e. inside frame
+    // (grid*base / L) / M: that frame and everything after it is zeroed by the host instead
+    sp.zero_frames = sp.rem > 0 ? (int)(((long long)grid * sp.base / p.L) / p.M) : p.N;
+}
+
+template <typename TV, typename TM>
+cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc, SortParams &sp, size_t smem, int grid, cudaStream_t st)
+{
     auto go = [&](auto kern_c) {
         constexpr auto kern = decltype(kern_c)::value;
         cudaError_t e = ensure_smem_optin<kern>(p);
         if (e != cudaSuccess) return e;
-        kern<<<grid, threads_for_split(kSplit, noslab ? kModeNoSlab : 0), smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (const TV *)io.grad_out, gv_acc,
+        kern<<<grid, threads_for_split(kSplit), smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (const TV *)io.grad_out, gv_acc,
                                                           (TM *)io.grad_loc, (TM *)io.grad_attn, (const TM *)p.ref, p.mask, sp);
         count_launch();
         return cudaGetLastError();
     };
     using std::integral_constant;
 #define MSDA_SORTED_KERN(PT, MD) integral_constant<decltype(&bwd_sorted32_kernel<TV, TM, PT, kSplit, MD>), &bwd_sorted32_kernel<TV, TM, PT, kSplit, MD>>()
-    if constexpr (std::is_same<TV, float>::value) {
-        if (noslab) {
-            if (sp.fused) return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeLeanFused | kModeNoSlab)) : go(MSDA_SORTED_KERN(0, kModeLeanFused | kModeNoSlab));
-            return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeLean | kModeNoSlab)) : go(MSDA_SORTED_KERN(0, kModeLean | kModeNoSlab));
-        }
+    if constexpr (std::is_same<TV, float>::value && std::is_same<TM, float>::value) {  // the fused prologue is float32-only
+        if (sp.fused) return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeLeanFused)) : go(MSDA_SORTED_KERN(0, kModeLeanFused));
     }
-    if (sp.fused) return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeLeanFused)) : go(MSDA_SORTED_KERN(0, kModeLeanFused));
+    if (sp.fused) return cudaErrorInvalidValue;
     return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeLean)) : go(MSDA_SORTED_KERN(0, kModeLean));
 #undef MSDA_SORTED_KERN
 }
@@ -718,26 +710,35 @@ bool sorted32_supported(const Problem &p)
 {
     SortParams sp;
     size_t smem;
-    bool noslab;
-    return make_params(p, sp, smem, noslab);
+    return make_params(p, sp, smem);
 }
 
 cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st)
 {
     SortParams sp;
     size_t smem;
-    bool noslab;
-    if (!make_params(p, sp, smem, noslab)) return cudaErrorInvalidValue;
+    if (!make_params(p, sp, smem)) return cudaErrorInvalidValue;
     const long long n_val = (long long)p.N * p.S * p.M * p.D;
     float *acc = p.dtype == 0 ? (float *)io.grad_value : (float *)io.workspace;  // bf16: fp32 accumulation in the workspace
-    if (n_val > 0) {
-        cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(float) * (size_t)n_val, st);
+    int grid = 1;
+    if (sp.units > 0 && p.Lq > 0) plan_units(p, sp, grid);
+    else sp.zero_frames = 0;
+    // the kernel zeroes what whole units own -- provided the levels tile [0, S) exactly, so that every pixel belongs to a unit
+    long long next = 0;
+    for (int l = 0; l < p.L; ++l) {
+        if (sp.start[l] != next) sp.zero_frames = 0;
+        next += (long long)sp.H[l] * sp.W[l];
+    }
+    if (next != p.S) sp.zero_frames = 0;
+    if (n_val > 0 && sp.zero_frames < p.N) {
+        const size_t frame = (size_t)p.S * p.M * p.D;
+        cudaError_t e = cudaMemsetAsync(acc + (size_t)sp.zero_frames * frame, 0, sizeof(float) * frame * (size_t)(p.N - sp.zero_frames), st);
         if (e != cudaSuccess) return e;
     }
     if (sp.units == 0 || p.Lq == 0) return cudaSuccess;
-    cudaError_t e = p.dtype == 0      ? launch_sorted<float, float>(p, io, acc, sp, smem, noslab, st)
-                    : p.loc_dtype == 0 ? launch_sorted<bf16, float>(p, io, acc, sp, smem, noslab, st)
-                                       : launch_sorted<bf16, bf16>(p, io, acc, sp, smem, noslab, st);
+    cudaError_t e = p.dtype == 0      ? launch_sorted<float, float>(p, io, acc, sp, smem, grid, st)
+                    : p.loc_dtype == 0 ? launch_sorted<bf16, float>(p, io, acc, sp, smem, grid, st)
+                                       : launch_sorted<bf16, bf16>(p, io, acc, sp, smem, grid, st);
     if (e != cudaSuccess) return e;
     if (p.dtype == 1) return convert_f32_to_bf16(acc, io.grad_value, n_val, p.sm_count, st);
     return cudaSuccess;

@@ -72,7 +72,7 @@ def test_workspace_query(lib):
     L = lib.load()
     assert L.msda_backward_workspace_bytes(0, 0, 40, 1029, 8, 32, 3, 1029, 4) == 0
     # no fp32 variant needs scratch, whichever is forced (the experimental pipe32 backward of round 1, which did, is gone)
-    assert L.msda_select_variant(1, b"split32") == 0
+    assert L.msda_select_variant(1, b"sorted32") == 0
     assert L.msda_backward_workspace_bytes(0, 0, 40, 1029, 8, 32, 3, 1029, 4) == 0
     assert L.msda_select_variant(1, b"pipe32") != 0
     assert L.msda_select_variant(1, b"auto") == 0
