@@ -24,6 +24,12 @@ import time
 
 # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ..." under NCCL_DEBUG=VERSION/INFO) is written to stdout by
 # the library itself, so its debug output is pointed at stderr before torch / NCCL are loaded
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "NCCL_DEBUG" not in os.environ and "NCCL_DEBUG_FILE" not in os.environ:
+    # multi-GPU run: ask NCCL's tuner to log which all-reduce algorithm it picks (per-rank file, parsed by nccl_algorithm_seen)
+    os.environ["MSDA_NCCL_LOG"] = "/tmp/msda_bench_nccl_%h_%p.log"
+    os.environ["NCCL_DEBUG_FILE"] = os.environ["MSDA_NCCL_LOG"]
+    os.environ["NCCL_DEBUG"] = "INFO"
+    os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,TUNING"
 os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
@@ -175,6 +181,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(n_frames, "f32"),
+        "note": "one host CPU complex times a bounded sample of ONE rank's batch whatever --gpus says (the CPU path does not shard "
+                "over GPUs): compare it with the N=1 line; at N>1 the ratio is N GPUs against the same single host",
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d of %d frames per step, fwd+bwd, torch %s CPU grid_sample path (oracle/core_pytorch.py)" % (sample, n_frames, torch.__version__)},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -189,6 +197,143 @@ def workload_config(n_frames, dtype):
             "frames_per_gpu": n_frames, "levels": S4_SHAPES, "heads": M, "points": P, "head_dim": D, "queries": LQ,
             "im2col_step": 128, "inputs": "value=U*0.01, loc=U[0,1), attn=normalised U (reference ops/test.py:36-39), seed 3",
             "l2": "%d rotating input/output sets (> 126 MB L2 each step cold)" % N_SETS, "value_dtype": dtype}
+
+
+
+# ------------------------------------------------------------------------------------- the reference's CUDA kernels, same tensors
+def time_incumbent(torch, pkg, sets, shapes, start, n_frames, dtype, loc_dtype, windows):
+    """fwd / bwd microseconds of the reference's own extension (ops/src/cuda/ms_deform_im2col_cuda.cuh:242-408, built unmodified
+    but for a two-line torch-2.x patch by oracle/build_ref.py into oracle/_ref/) and its max-norm relative difference from ours."""
+    if dtype != torch.float32 or loc_dtype != torch.float32:
+        return {"unavailable": "the reference extension is float32 / float64 only"}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import build_ref
+        ref = build_ref.load_ref()
+    except Exception as e:  # pragma: no cover - depends on the box
+        return {"unavailable": "oracle/_ref failed to load: %s" % e}
+    finally:
+        sys.path.pop(0)
+    if ref is None:
+        return {"unavailable": "oracle/_ref/MultiScaleDeformableAttention.so did not travel (build it with python oracle/build_ref.py)"}
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+    v, l, a, g = sets[0]
+    out_r = ref.ms_deform_attn_forward(v, shapes, start, l, a, 128)
+    gv_r, gl_r, ga_r = ref.ms_deform_attn_backward(v, shapes, start, l, a, g, 128)
+    out = pkg.ms_deform_attn_forward(v, shapes, start, l, a, 128)
+    gv, gl, ga = pkg.ms_deform_attn_backward(v, shapes, start, l, a, g, 128)
+    diffs = {"out": rel(out, out_r), "grad_value": rel(gv, gv_r), "grad_sampling_loc": rel(gl, gl_r), "grad_attn_weight": rel(ga, ga_r)}
+    del out_r, gv_r, gl_r, ga_r, out, gv, gl, ga
+
+    def timed(fn, reps):
+        for i in range(3):
+            fn(*sets[i % N_SETS])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(reps):
+            fn(*sets[i % N_SETS])
+        e1.record()
+        torch.cuda.synchronize()
+        windows.append((t0, time.time()))
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    us_f = timed(lambda v, l, a, g: ref.ms_deform_attn_forward(v, shapes, start, l, a, 128), 40)
+    us_b = timed(lambda v, l, a, g: ref.ms_deform_attn_backward(v, shapes, start, l, a, g, 128), 20)
+    return {"what": "the reference's own CUDA extension (oracle/_ref, ms_deform_im2col_cuda.cuh kernels) on the same tensors and GPU",
+            "fwd_us": us_f, "bwd_us": us_b, "fwd_bwd_us": us_f + us_b, "frames_per_s": n_frames / ((us_f + us_b) * 1e-6),
+            "max_rel_diff_vs_ours": diffs, "allocations": "callee-allocated outputs (at::zeros), as the reference does"}
+
+
+# --------------------------------------------------------------------------- the caller: pixel-decoder DDP training step
+def time_model_step(torch, dist, pkg, dev, rank, world, windows, iters=8):
+    """Training step (forward + backward + fused AdamW, fp32 like the reference: AMP is off for S4/MS3 and msdeformattn.py:321 forces
+    float) of the COMBO-R50 S4 MSDeformAttnPixelDecoder (msdeformattn.py:169-368: input projections + GroupNorm, 6 deformable encoder
+    layers = 6 calls of the op each way, FPN top-down pass, mask features) on synthetic ResNet-50-shaped features of 224x224 frames,
+    one process per GPU under DistributedDataParallel.  weak: 8 clips x 5 frames per GPU; strong: a global batch of 8 clips sharded
+    by clip (detectron2 semantics, train_net.py:117).  The backbones, audio branch, transformer decoder and criterion of the full
+    model are NOT in this step (tools/combo_harness.py holds the full-model harness)."""
+    from combo_avs_b200.pixel_decoder import MSDeformAttnPixelDecoder
+    from combo_avs_b200.sharding import max_over_ranks, shard_clips
+    r50 = {"res2": (256, 4), "res3": (512, 8), "res4": (1024, 16), "res5": (2048, 32)}
+    torch.manual_seed(7)
+    top = MSDeformAttnPixelDecoder(r50, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
+                                   transformer_enc_layers=6, conv_dim=256, mask_dim=256, norm="GN",
+                                   transformer_in_features=["res3", "res4", "res5"], common_stride=4).to(dev)
+    with torch.no_grad():  # off the zero init, so offsets / weights vary per query as in a trained model
+        for layer in top.transformer.encoder.layers:
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.02)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.1)
+    model = torch.nn.parallel.DistributedDataParallel(top, device_ids=[dev.index]) if world > 1 else top
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, fused=True)
+    grad_bytes = sum(p.numel() * p.element_size() for p in top.parameters() if p.requires_grad)
+    res = {"model": "COMBO-R50 S4 MSDeformAttnPixelDecoder (6 deformable encoder layers, conv_dim 256, FFN 1024), fp32, fwd+bwd+AdamW",
+           "unit": "frames/s", "n_gpus": world, "parameters": sum(p.numel() for p in top.parameters()),
+           "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
+           "collective": ("DistributedDataParallel gradient all-reduce, NCCL %s, bucket_cap 25 MiB; algorithm: %s"
+                          % (".".join(map(str, torch.cuda.nccl.version())), nccl_algorithm_seen())) if world > 1 else "none (1 GPU)"}
+    l0 = pkg.launch_count()
+    for mode in ("weak", "strong"):
+        frames = 40 if mode == "weak" else shard_clips(8, 5, rank, world)[1]
+        if frames == 0:  # more GPUs than clips: this rank idles in the strong-scaling leg but still joins the all-reduce
+            frames = 0
+        g = torch.Generator().manual_seed(100 + rank)
+        feats = {k: torch.randn(max(frames, 1), c, 224 // s, 224 // s, generator=g).to(dev) for k, (c, s) in r50.items()}
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            mask_feat, low, multi = model(feats)
+            (mask_feat.mean() + low.mean() + sum(m.mean() for m in multi)).backward()
+            opt.step()
+
+        for _ in range(3):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        windows.append((t0, time.time()))
+        ms = max_over_ranks(e0.elapsed_time(e1), dev) / iters
+        total_frames = world * 40 if mode == "weak" else 40
+        res[mode] = {"frames_per_gpu": frames, "global_frames": total_frames, "ms_per_step": ms, "value": total_frames / (ms * 1e-3)}
+        del feats
+    res["msda_launches_per_step"] = (pkg.launch_count() - l0) / (2 * (iters + 3))
+    del model, top, opt
+    torch.cuda.empty_cache()
+    return res
+
+
+def nccl_algorithm_seen():
+    """Best effort: the algorithm NCCL's tuner picked for the largest all-reduce, parsed from this rank's NCCL_DEBUG=INFO /
+    NCCL_DEBUG_SUBSYS=TUNING log when bench.py was allowed to request one (see main)."""
+    path = os.environ.get("MSDA_NCCL_LOG")
+    names = {0: "Tree", 1: "Ring", 2: "CollnetDirect", 3: "CollnetChain", 4: "NVLS", 5: "NVLSTree", 6: "PAT"}
+    best = None
+    try:
+        import glob
+        import re
+        for f in glob.glob(path.replace("%h", "*").replace("%p", "*")) if path else []:
+            for line in open(f, errors="replace"):
+                m = re.search(r"AllReduce: (\d+) Bytes -> Algo (\d+) proto (\d+)", line)
+                if m and (best is None or int(m.group(1)) > best[0]):
+                    best = (int(m.group(1)), int(m.group(2)), int(m.group(3)))
+    except Exception:
+        best = None
+    if best is None:
+        return "chosen by NCCL's tuner (not logged in this run)"
+    return "%s, protocol %s for the %d-byte bucket (NCCL tuner log)" % (names.get(best[1], "algo %d" % best[1]), {0: "LL", 1: "LL128", 2: "Simple"}.get(best[2], best[2]), best[0])
 
 
 # ------------------------------------------------------------------------------------------------------- GPU arm
@@ -284,6 +429,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": "%s (%s)" % (dom[0], pkg.last_variant(dom[0])), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": (load_traffic(pkg.last_variant(dom[0]) + ("" if args.dtype == "fp32" else "_bf16")) or {}).get("dram_bytes_per_launch")
                 if nF == 40 and (args.dtype == "fp32" or loc_dtype == torch.float32) else None,
+                "traffic_source": "constant: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture "
+                                  "(profiles/traffic.json), not measured in this run",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom[1], "us_per_launch": dom[2],
                 "fwd": {"us": us_f, "bytes": bytes_f, "GBps": bytes_f / us_f / 1e3, "frac": bytes_f / us_f / 1e3 / peak, "variant": pkg.last_variant("forward")},
@@ -315,6 +462,18 @@ def run_ours(args):
     e2e = {"value": world * nF / e2e_s, "unit": UNIT, "h2d_bytes_per_step": xfer["h2d"], "d2h_bytes_per_step": xfer["d2h"],
            "ms_per_step": e2e_s * 1e3, "api": "combo_avs_b200.host_api.HostPipeline.forward_backward -> msda_forward_backward_host (C ABI; pinned host tensors, %d-frame chunks, 3 streams, 3 staging slots)" % args.e2e_chunk}
 
+    # ---- the incumbent: the reference's own CUDA kernels (oracle/_ref, compiled from /root/reference by oracle/build_ref.py) on the
+    # same tensors, same GPU -- measurement infrastructure only, nothing of it is on the product path
+    incumbent = None
+    if rank == 0 and world == 1 and not args.no_incumbent:
+        incumbent = time_incumbent(torch, pkg, sets, shapes, start, nF, dtype, loc_dtype, windows)
+
+    # ---- one level up: the DDP training step of the pixel decoder that calls the op 6x per pass (weak: 8 clips per GPU; strong:
+    # a global batch of 8 clips sharded by clip, train_net.py:117) -- NCCL gradient all-reduce is the only collective
+    model_step = None
+    if not args.no_model_step and dtype == torch.float32:
+        model_step = time_model_step(torch, dist, pkg, dev, rank, world, windows)
+
     clocks = sampler.stop(windows) if sampler else None
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only): bounded sample of the same workload ---------------------
@@ -340,8 +499,9 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "bf16",
-                "data": "synthetic", "config": workload_config(nF, args.dtype), "fwd_bwd_us": ms_step * 1e3,
+                "data": "synthetic", "config": workload_config(nF, "f32" if dtype == torch.float32 else "bf16"), "fwd_bwd_us": ms_step * 1e3,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "incumbent": incumbent, "model_step": model_step,
                 "variants": {"forward": pkg.last_variant("forward"), "backward": pkg.last_variant("backward")}}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -362,6 +522,8 @@ def main():
     ap.add_argument("--bwd-variant", default=None)
     ap.add_argument("--e2e-chunk", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the reference-CUDA-extension leg")
+    ap.add_argument("--no-model-step", action="store_true", help="skip the pixel-decoder DDP training-step leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -75,5 +75,28 @@ def load_ref():
     return mod
 
 
+OPS = "/root/reference/models/modeling/pixel_decoder/ops"
+OPS_TEST_DIR = os.path.join(OUT, "ops_test")
+
+
+def stage_ops_test(force=False):
+    """Byte-compile the reference's own, UNMODIFIED ops/test.py (test.py:24-96) and the module it imports
+    (functions/ms_deform_attn_func.py: the reference's MSDeformAttnFunction + ms_deform_attn_core_pytorch) into
+    oracle/_ref/ops_test/ as sourceless .pyc files -- compiled outputs like the .so, never sources -- so that the GPU box, where
+    /root/reference does not exist, can run the reference's test against the shim module `MultiScaleDeformableAttention`
+    (tests/test_gpu_parity.py::test_reference_ops_test_runs_unmodified_through_the_shim).  Returns the path of test.pyc or None."""
+    target = os.path.join(OPS_TEST_DIR, "test.pyc")
+    if os.path.exists(target) and not force:
+        return target
+    if not os.path.isdir(OPS):
+        return target if os.path.exists(target) else None
+    import py_compile
+    os.makedirs(os.path.join(OPS_TEST_DIR, "functions"), exist_ok=True)
+    for rel in ("test.py", os.path.join("functions", "__init__.py"), os.path.join("functions", "ms_deform_attn_func.py")):
+        py_compile.compile(os.path.join(OPS, rel), cfile=os.path.join(OPS_TEST_DIR, rel + "c"), dfile="reference:ops/" + rel, doraise=True)
+    return target
+
+
 if __name__ == "__main__":
     print(build_ref(force="--force" in sys.argv))
+    print(stage_ops_test(force="--force" in sys.argv))
