@@ -76,25 +76,36 @@ def load_ref():
 
 
 OPS = "/root/reference/models/modeling/pixel_decoder/ops"
-OPS_TEST_DIR = os.path.join(OUT, "ops_test")
+OPS_TEST_ZIP = os.path.join(OUT, "ops_test.zip")
 
 
 def stage_ops_test(force=False):
     """Byte-compile the reference's own, UNMODIFIED ops/test.py (test.py:24-96) and the module it imports
-    (functions/ms_deform_attn_func.py: the reference's MSDeformAttnFunction + ms_deform_attn_core_pytorch) into
-    oracle/_ref/ops_test/ as sourceless .pyc files -- compiled outputs like the .so, never sources -- so that the GPU box, where
+    (functions/ms_deform_attn_func.py: the reference's MSDeformAttnFunction + ms_deform_attn_core_pytorch) into one archive of
+    sourceless bytecode, oracle/_ref/ops_test.zip -- a compiled output like the .so, never sources -- so that the GPU box, where
     /root/reference does not exist, can run the reference's test against the shim module `MultiScaleDeformableAttention`
-    (tests/test_gpu_parity.py::test_reference_ops_test_runs_unmodified_through_the_shim).  Returns the path of test.pyc or None."""
-    target = os.path.join(OPS_TEST_DIR, "test.pyc")
-    if os.path.exists(target) and not force:
-        return target
+    (`python oracle/_ref/ops_test.zip`; tests/test_gpu_parity.py::test_reference_ops_test_runs_unmodified_through_the_shim).
+    test.py becomes the archive's __main__.  Returns the path of the archive or None."""
+    if os.path.exists(OPS_TEST_ZIP) and not force:
+        return OPS_TEST_ZIP
     if not os.path.isdir(OPS):
-        return target if os.path.exists(target) else None
+        return None
     import py_compile
-    os.makedirs(os.path.join(OPS_TEST_DIR, "functions"), exist_ok=True)
-    for rel in ("test.py", os.path.join("functions", "__init__.py"), os.path.join("functions", "ms_deform_attn_func.py")):
-        py_compile.compile(os.path.join(OPS, rel), cfile=os.path.join(OPS_TEST_DIR, rel + "c"), dfile="reference:ops/" + rel, doraise=True)
-    return target
+    import zipfile
+    tmp = tempfile.mkdtemp(prefix="msda_ops_test_")
+    try:
+        members = (("test.py", "__main__.pyc"), (os.path.join("functions", "__init__.py"), "functions/__init__.pyc"),
+                   (os.path.join("functions", "ms_deform_attn_func.py"), "functions/ms_deform_attn_func.pyc"))
+        os.makedirs(OUT, exist_ok=True)
+        with zipfile.ZipFile(OPS_TEST_ZIP + ".tmp", "w") as z:
+            for src, arc in members:
+                cfile = os.path.join(tmp, arc.replace("/", "_"))
+                py_compile.compile(os.path.join(OPS, src), cfile=cfile, dfile="reference:ops/" + src, doraise=True)
+                z.write(cfile, arc)
+        os.replace(OPS_TEST_ZIP + ".tmp", OPS_TEST_ZIP)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return OPS_TEST_ZIP
 
 
 if __name__ == "__main__":

@@ -345,9 +345,9 @@ def test_reference_ops_test_runs_unmodified_through_the_shim():
     _, build_ref = _load_incumbent()
     test_pyc = build_ref.stage_ops_test()
     if test_pyc is None:
-        pytest.skip("LOUD SKIP: oracle/_ref/ops_test/test.pyc did not travel -- run `python oracle/build_ref.py` where /root/reference exists")
+        pytest.skip("LOUD SKIP: oracle/_ref/ops_test.zip did not travel -- run `python oracle/build_ref.py` where /root/reference exists")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "combo-avs_b200", "shim"), root, os.environ.get("PYTHONPATH", "")]))
-    r = subprocess.run([sys.executable, test_pyc], cwd=os.path.dirname(test_pyc), env=env, capture_output=True, text=True, timeout=1500)
+    r = subprocess.run([sys.executable, test_pyc], cwd=root, env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = [x for x in r.stdout.splitlines() if x.startswith("* ")]
     assert len(lines) == 9, r.stdout + r.stderr           # 2 forward checks + 7 gradcheck widths
