@@ -24,7 +24,8 @@ import time
 
 # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ..." under NCCL_DEBUG=VERSION/INFO) is written to stdout by
 # the library itself, so its debug output is pointed at stderr before torch / NCCL are loaded
-if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "NCCL_DEBUG" not in os.environ and "NCCL_DEBUG_FILE" not in os.environ:
+if (int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN")
+        and "NCCL_DEBUG_FILE" not in os.environ):
     # multi-GPU run: ask NCCL's tuner to log which all-reduce algorithm it picks (per-rank file, parsed by nccl_algorithm_seen)
     os.environ["MSDA_NCCL_LOG"] = "/tmp/msda_bench_nccl_%h_%p.log"
     os.environ["NCCL_DEBUG_FILE"] = os.environ["MSDA_NCCL_LOG"]
@@ -274,8 +275,7 @@ def time_model_step(torch, dist, pkg, dev, rank, world, windows, iters=8):
     res = {"model": "COMBO-R50 S4 MSDeformAttnPixelDecoder (6 deformable encoder layers, conv_dim 256, FFN 1024), fp32, fwd+bwd+AdamW",
            "unit": "frames/s", "n_gpus": world, "parameters": sum(p.numel() for p in top.parameters()),
            "allreduce_bytes_per_step": grad_bytes if world > 1 else 0,
-           "collective": ("DistributedDataParallel gradient all-reduce, NCCL %s, bucket_cap 25 MiB; algorithm: %s"
-                          % (".".join(map(str, torch.cuda.nccl.version())), nccl_algorithm_seen())) if world > 1 else "none (1 GPU)"}
+           "collective": "none (1 GPU)"}
     l0 = pkg.launch_count()
     for mode in ("weak", "strong"):
         frames = 40 if mode == "weak" else shard_clips(8, 5, rank, world)[1]
@@ -311,6 +311,9 @@ def time_model_step(torch, dist, pkg, dev, rank, world, windows, iters=8):
         res[mode] = {"frames_per_gpu": frames, "global_frames": total_frames, "ms_per_step": ms, "value": total_frames / (ms * 1e-3)}
         del feats
     res["msda_launches_per_step"] = (pkg.launch_count() - l0) / ((2 if world > 1 else 1) * (iters + 3))
+    if world > 1:  # (asked after the all-reduces have run: NCCL's tuner logs its choice at the first collective of each size)
+        res["collective"] = ("DistributedDataParallel gradient all-reduce, NCCL %s, bucket_cap 25 MiB; algorithm: %s"
+                             % (".".join(map(str, torch.cuda.nccl.version())), nccl_algorithm_seen()))
     del model, top, opt
     torch.cuda.empty_cache()
     try:
@@ -378,21 +381,22 @@ def nccl_algorithm_seen():
     """Best effort: the algorithm NCCL's tuner picked for the largest all-reduce, parsed from this rank's NCCL_DEBUG=INFO /
     NCCL_DEBUG_SUBSYS=TUNING log when bench.py was allowed to request one (see main)."""
     path = os.environ.get("MSDA_NCCL_LOG")
-    names = {0: "Tree", 1: "Ring", 2: "CollnetDirect", 3: "CollnetChain", 4: "NVLS", 5: "NVLSTree", 6: "PAT"}
+    names = {"0": "Tree", "1": "Ring", "2": "CollnetDirect", "3": "CollnetChain", "4": "NVLS", "5": "NVLSTree", "6": "PAT"}
+    protos = {"0": "LL", "1": "LL128", "2": "Simple"}
     best = None
     try:
         import glob
         import re
         for f in glob.glob(path.replace("%h", "*").replace("%p", "*")) if path else []:
             for line in open(f, errors="replace"):
-                m = re.search(r"AllReduce: (\d+) Bytes -> Algo (\d+) proto (\d+)", line)
+                m = re.search(r"AllReduce: (\d+) Bytes -> Algo (\w+) proto (\w+)", line)
                 if m and (best is None or int(m.group(1)) > best[0]):
-                    best = (int(m.group(1)), int(m.group(2)), int(m.group(3)))
+                    best = (int(m.group(1)), m.group(2), m.group(3))
     except Exception:
         best = None
     if best is None:
         return "chosen by NCCL's tuner (not logged in this run)"
-    return "%s, protocol %s for the %d-byte bucket (NCCL tuner log)" % (names.get(best[1], "algo %d" % best[1]), {0: "LL", 1: "LL128", 2: "Simple"}.get(best[2], best[2]), best[0])
+    return "%s, protocol %s for the %d-byte bucket (NCCL tuner log)" % (names.get(best[1], best[1]), protos.get(best[2], best[2]), best[0])
 
 
 # ------------------------------------------------------------------------------------------------------- GPU arm
