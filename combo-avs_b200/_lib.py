@@ -28,6 +28,8 @@ EXPORTS = (
     "msda_fused_supported",
     "msda_fused_forward",
     "msda_fused_backward",
+    "msda_linear_supported",
+    "msda_linear_forward",
 )
 
 _lib = None
@@ -69,6 +71,10 @@ def load():
     lib.msda_last_error.restype = ctypes.c_char_p
     lib.msda_version.argtypes = []
     lib.msda_version.restype = i
+    lib.msda_linear_supported.argtypes = [i, i, i]
+    lib.msda_linear_supported.restype = i
+    lib.msda_linear_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.msda_linear_forward.restype = i
     lib.msda_host_pipeline_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), i, i, i]
     lib.msda_host_pipeline_create.restype = i
     lib.msda_host_pipeline_destroy.argtypes = [vp]

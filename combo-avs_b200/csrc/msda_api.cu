@@ -354,4 +354,29 @@ int msda_fused_backward(int dtype, const void *value, const int64_t *spatial_sha
     return MSDA_OK;
 }
 
+/* ---- encoder-layer Linear on the tensor cores (msdeformattn.py:119-134, ms_deform_attn.py:105-128) ------------------ */
+
+int msda_linear_supported(int M, int N, int K) { return linear_supported(M, N, K) ? 1 : 0; }
+
+int msda_linear_forward(const void *x, const void *weight, const void *bias, void *y, int M, int N, int K, int flags, int device, void *stream)
+{
+    if (M < 0 || N <= 0 || K <= 0) return fail(MSDA_ERR_DIM, "bad dimensions M=%d N=%d K=%d", M, N, K);
+    if (M == 0) return MSDA_OK;
+    if (!x || !weight || !y) return fail(MSDA_ERR_NULL, "NULL pointer in msda_linear_forward");
+    DeviceInfo di;
+    int rc = device_info(device, di);
+    if (rc != MSDA_OK) return rc;
+    if (!linear_supported(M, N, K))
+        return fail(MSDA_ERR_VARIANT, "msda_linear_forward needs K %% 4 == 0, N %% 16 == 0 and a driver with cuTensorMapEncodeTiled (M=%d N=%d K=%d)", M, N, K);
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias)) & 15)
+        return fail(MSDA_ERR_DIM, "msda_linear_forward needs 16-byte aligned pointers");
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    e = linear_tf32((const float *)x, (const float *)weight, (const float *)bias, (float *)y, M, N, K, flags & MSDA_LINEAR_RELU,
+                    (flags & MSDA_LINEAR_TF32_ONLY) ? 0 : 1, device, di.sm_count, di.smem_optin, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "msda_linear_forward launch");
+    return MSDA_OK;
+}
+
 }  // extern "C"

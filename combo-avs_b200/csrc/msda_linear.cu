@@ -1,0 +1,374 @@
+// msda_linear.cu -- row f2 of the scope table: the Linear layers AROUND the op in the deformable encoder layer
+// (reference models/modeling/pixel_decoder/msdeformattn.py:119-134: linear1 256->1024, linear2 1024->256;
+//  ops/modules/ms_deform_attn.py:105-128: value_proj / sampling_offsets / attention_weights / output_proj) on the 5th-generation
+// tensor cores, at float32 accuracy.
+//
+// The reference runs these GEMMs in strict fp32 (AMP is off for S4 / MS3, matmul.allow_tf32 False): 1.1 TFLOP per encoder training step
+// on the SIMT pipes, 85 % of the step.  Here every float32 operand is split into two TF32-representable halves,
+// x = hi + lo with hi = x with its 13 low mantissa bits cleared and lo = x - hi (exact), and
+//     x * w  ~=  hi_x*hi_w + hi_x*lo_w + lo_x*hi_w            (the dropped lo*lo term is below 2^-21 relative)
+// is accumulated in float32 in tensor memory by three tcgen05.mma.kind::tf32 per 8-wide K step ("3xTF32").
+//
+// Kernel (one persistent CTA per SM, warp-specialised, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled boxes of A [128 x 32] and W [BN x 32] into a ring of stages
+//   warps 2-5   splitters: when a stage has landed, rewrite it in place as `hi` and write `lo` next to it (shared memory only),
+//               fence.proxy.async, hand the stage to
+//   warp 1      the MMA issuer: one elected lane issues 3 x 4 tcgen05.mma (M=128, N=BN, K=8) per stage into one of two TMEM accumulators,
+//               tcgen05.commit releases the stage to the producer and, after the last K block, the accumulator to
+//   warps 6-9   the epilogue: tcgen05.ld the accumulator (lane = row), add the bias (optionally ReLU), store float32 rows;
+//               the other accumulator is being filled meanwhile.
+// C[M, N] = A[M, K] . W[N, K]^T + bias[N]; the same kernel serves the forward (W = weight) and dgrad (W = weight^T, no bias).
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
+#include "../../include/msda_b200.h"
+#include "msda_kernels.h"
+#include "msda_tma.cuh"
+
+namespace msda {
+namespace {
+
+constexpr int kBM = 128;          // rows of A per tile = TMEM lanes
+constexpr int kBK = 32;           // floats per K block = one 128-byte swizzle row
+constexpr int kUmmaK = 8;         // K of one tcgen05.mma.kind::tf32
+constexpr int kThreads = 320;
+constexpr int kSplitWarp0 = 2, kEpiWarp0 = 6;
+
+struct LinearParams {
+    int M, N, K;
+    int BN;            // columns of C per tile (multiple of 16, <= 256, divides N)
+    int stages;
+    int split;         // 1: 3xTF32 (float32 accuracy); 0: plain TF32 (profiling / bring-up only)
+    int relu;
+    int ksplit;        // > 1: the K blocks of a tile are shared out over `ksplit` work items, which ADD their partial sums into a zeroed C
+    int kb_total, kb_per;
+    int tiles_m, tiles_n;
+    unsigned stage_bytes, a_bytes, b_bytes;
+};
+
+struct alignas(64) LinearMaps {
+    CUtensorMap a, w;
+};
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 2-D box of a tiled tensor map -> shared memory
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+// shared-memory matrix descriptor of a K-major tile whose rows are one 128-byte swizzle span (cute::UMMA::SmemDescriptor):
+// start address >> 4 in bits [0,14), stride between 8-row groups (1024 B) >> 4 in bits [32,46), version 1 in bits [46,48),
+// layout SWIZZLE_128B (2) in bits [61,64); the leading-dimension offset is not used by this layout
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr)
+{
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr & 0x3ffff) >> 4);
+    d |= (unsigned long long)(1024 >> 4) << 32;
+    d |= 1ULL << 46;
+    d |= 2ULL << 61;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ unsigned umma_idesc(int m, int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// all tcgen05.mma issued so far by this thread arrive on `bar` when they have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(unsigned bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16])
+{
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const __grid_constant__ LinearParams lp,
+                   const __grid_constant__ LinearMaps maps)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    // stage s: [A hi 16 KB][W hi b_bytes] (and, with split: [A lo][W lo]) -- every tile 1024-byte aligned for the 128-byte swizzle
+    // (the 128-byte swizzle wants 1024-byte aligned tiles; the launch reserves the slack for rounding the base up)
+    const unsigned smem_raw = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned pad = (1024u - (smem_raw & 1023u)) & 1023u;
+    unsigned char *smem_al = smem + pad;
+    const unsigned smem_s = smem_raw + pad;
+    const unsigned bars = smem_s + lp.stages * lp.stage_bytes;   // full[s], ready[s], empty[s], tmem_full[2], tmem_empty[2], tmem base
+    auto full = [&](int s) { return bars + 8 * s; };
+    auto ready = [&](int s) { return bars + 8 * (lp.stages + s); };
+    auto empty = [&](int s) { return bars + 8 * (2 * lp.stages + s); };
+    auto tfull = [&](int b) { return bars + 8 * (3 * lp.stages + b); };
+    auto tempty = [&](int b) { return bars + 8 * (3 * lp.stages + 2 + b); };
+    unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem_al + lp.stages * lp.stage_bytes + 8 * (3 * lp.stages + 4));
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = lp.tiles_m * lp.tiles_n * lp.ksplit;
+    // work item t -> (tile row, tile column, K slice): its K blocks are [kb0, kb0 + kblocks)
+    auto decode = [&](int t, int &tm, int &tn, int &kb0, int &kblocks) {
+        const int ks = t % lp.ksplit;
+        const int tt = t / lp.ksplit;
+        tm = tt / lp.tiles_n;
+        tn = tt - tm * lp.tiles_n;
+        kb0 = ks * lp.kb_per;
+        kblocks = min(lp.kb_per, lp.kb_total - kb0);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < lp.stages; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(ready(s), 4);   // one arrival per splitter warp
+            mbar_init(empty(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull(b), 1);
+            mbar_init(tempty(b), 4);  // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (wid == 1) {  // the MMA warp owns the tensor-memory allocation: 512 columns = two float32 accumulators of up to 256 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    if (wid == 0) {
+        // ---- TMA producer ---------------------------------------------------------------------------------------------------
+        if (lane == 0) {
+            tma_prefetch_map(&maps.a);
+            tma_prefetch_map(&maps.w);
+            int it = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                int tm, tn, kb0, kblocks;
+                decode(t, tm, tn, kb0, kblocks);
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % lp.stages, round = it / lp.stages;
+                    if (round > 0) mbar_wait(empty(s), (unsigned)((round - 1) & 1));
+                    const unsigned base = smem_s + s * lp.stage_bytes;
+                    mbar_arrive_expect_tx(full(s), lp.a_bytes + lp.b_bytes);
+                    tma_load_2d(base, &maps.a, full(s), (kb0 + kb) * kBK, tm * kBM);       // (columns past K arrive as zeros)
+                    tma_load_2d(base + lp.a_bytes, &maps.w, full(s), (kb0 + kb) * kBK, tn * lp.BN);
+                }
+            }
+        }
+    } else if (wid == 1) {
+        // ---- MMA issuer -----------------------------------------------------------------------------------------------------
+        const unsigned idesc = umma_idesc(kBM, lp.BN);
+        int it = 0, lt = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++lt) {
+            int tm, tn, kb0, kblocks;
+            decode(t, tm, tn, kb0, kblocks);
+            const int buf = lt & 1, use = lt >> 1;
+            if (use > 0) mbar_wait(tempty(buf), (unsigned)((use - 1) & 1));  // the epilogue has drained this accumulator
+            tc_fence_after();
+            const unsigned tmem_d = tmem_base + buf * 256;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                const int s = it % lp.stages, round = it / lp.stages;
+                mbar_wait(lp.split ? ready(s) : full(s), (unsigned)(round & 1));
+                tc_fence_after();
+                if (lane == 0) {
+                    const unsigned a_hi = smem_s + s * lp.stage_bytes, w_hi = a_hi + lp.a_bytes;
+                    const unsigned a_lo = w_hi + lp.b_bytes, w_lo = a_lo + lp.a_bytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const unsigned koff = k * kUmmaK * 4;  // bytes along the swizzled 128-byte row
+                        const unsigned long long dah = umma_desc(a_hi + koff), dwh = umma_desc(w_hi + koff);
+                        umma_tf32(tmem_d, dah, dwh, idesc, (kb | k) != 0);
+                        if (lp.split) {
+                            const unsigned long long dal = umma_desc(a_lo + koff), dwl = umma_desc(w_lo + koff);
+                            umma_tf32(tmem_d, dah, dwl, idesc, 1);
+                            umma_tf32(tmem_d, dal, dwh, idesc, 1);
+                        }
+                    }
+                    umma_commit(empty(s));                       // the stage is free once these MMAs have read it
+                    if (kb == kblocks - 1) umma_commit(tfull(buf));  // ... and after the last K block the accumulator is complete
+                }
+                __syncwarp();
+            }
+        }
+    } else if (wid < kEpiWarp0) {
+        // ---- splitters: x -> (hi, lo) in shared memory --------------------------------------------------------------------------
+        if (lp.split) {
+            const int st = threadIdx.x - kSplitWarp0 * 32;  // 0..127
+            int it = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                int tm, tn, kb0, kblocks;
+                decode(t, tm, tn, kb0, kblocks);
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % lp.stages, round = it / lp.stages;
+                    mbar_wait(full(s), (unsigned)(round & 1));
+                    unsigned char *base = smem_al + (size_t)s * lp.stage_bytes;
+                    const unsigned hi_bytes = lp.a_bytes + lp.b_bytes;  // [A | W] is contiguous, and so is [A lo | W lo] behind it
+                    float4 *hi = reinterpret_cast<float4 *>(base);
+                    float4 *lo = reinterpret_cast<float4 *>(base + hi_bytes);
+                    const unsigned n16 = hi_bytes / 16;  // four 16-byte chunks per thread per round: the loads of a round go out together
+                    for (unsigned i0 = st; i0 < n16; i0 += 4 * 128) {
+                        float4 x[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (i0 + r * 128 < n16) x[r] = hi[i0 + r * 128];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (i0 + r * 128 >= n16) break;
+                            float4 h, l;
+                            h.x = __uint_as_float(__float_as_uint(x[r].x) & 0xffffe000u); l.x = x[r].x - h.x;
+                            h.y = __uint_as_float(__float_as_uint(x[r].y) & 0xffffe000u); l.y = x[r].y - h.y;
+                            h.z = __uint_as_float(__float_as_uint(x[r].z) & 0xffffe000u); l.z = x[r].z - h.z;
+                            h.w = __uint_as_float(__float_as_uint(x[r].w) & 0xffffe000u); l.w = x[r].w - h.w;
+                            hi[i0 + r * 128] = h;   // (the swizzle permutes 16-byte chunks: an element-wise rewrite keeps the layout)
+                            lo[i0 + r * 128] = l;
+                        }
+                    }
+                    fence_proxy_async();  // these generic-proxy writes are read by the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ready(s));
+                }
+            }
+        }
+    } else {
+        // ---- epilogue: TMEM -> registers -> + bias -> global -------------------------------------------------------------------------
+        const int q = wid & 3;                        // a warp reads the TMEM lanes 32*(warp id % 4) ...
+        const int row_in_tile = q * 32 + lane;
+        int lt = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++lt) {
+            int tm, tn, kb0, kblocks;
+            decode(t, tm, tn, kb0, kblocks);
+            const int buf = lt & 1, use = lt >> 1;
+            mbar_wait(tfull(buf), (unsigned)(use & 1));
+            tc_fence_after();
+            const int row = tm * kBM + row_in_tile;
+            float *crow = C + (size_t)row * lp.N + tn * lp.BN;
+            const float *brow = (bias && kb0 == 0) ? bias + tn * lp.BN : nullptr;  // (split K: the first slice carries the bias)
+            const unsigned taddr = tmem_base + buf * 256 + ((unsigned)(q * 32) << 16);
+            for (int c0 = 0; c0 < lp.BN; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (row < lp.M) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (brow) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(brow + c0 + j));
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        if (lp.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        if (lp.ksplit > 1) red_add_v4(crow + c0 + j, o.x, o.y, o.z, o.w);
+                        else *reinterpret_cast<float4 *>(crow + c0 + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+bool make_map_2d(CUtensorMap *map, const float *base, int rows, int cols, int box_rows)
+{
+    EncodeTiledFn enc = tma_encode_fn();
+    if (enc == nullptr || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int pick_bn(int N)
+{
+    static const int bn_max = [] { const char *e = getenv("MSDA_LINEAR_BN_MAX"); const int v = e ? atoi(e) : 256; return v >= 16 && v <= 256 ? v & ~15 : 256; }();  // A/B switch
+    for (int bn = bn_max; bn >= 16; bn -= 16)
+        if (N % bn == 0) return bn;
+    return 0;
+}
+
+}  // namespace
+
+bool linear_supported(int M, int N, int K)
+{
+    // K % 4: the row pitch of x / weight must be a multiple of 16 bytes for the tensor maps (the K tail is zero-filled by TMA)
+    return M > 0 && N > 0 && K > 0 && K % 4 == 0 && N % 16 == 0 && pick_bn(N) >= 16 && tma_encode_fn() != nullptr;
+}
+
+cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float *C, int M, int N, int K, int relu, int split, int device,
+                        int sm_count, int smem_optin, cudaStream_t st)
+{
+    LinearParams lp;
+    lp.M = M; lp.N = N; lp.K = K;
+    lp.BN = pick_bn(N);
+    lp.split = split ? 1 : 0;
+    lp.relu = relu ? 1 : 0;
+    lp.tiles_m = (M + kBM - 1) / kBM;
+    lp.tiles_n = N / lp.BN;
+    lp.kb_total = (K + kBK - 1) / kBK;
+    // split K when the output alone cannot fill the GPU (the weight gradient: a few tiles, tens of thousands of K): C is zeroed
+    // first and every slice adds its partial tile with red.global.add.v4.f32
+    lp.ksplit = 1;
+    if (!relu && lp.tiles_m * lp.tiles_n * 2 <= sm_count && lp.kb_total >= 16) {
+        lp.ksplit = sm_count / (lp.tiles_m * lp.tiles_n);
+        if (lp.ksplit > lp.kb_total / 4) lp.ksplit = lp.kb_total / 4;
+        if (lp.ksplit < 1) lp.ksplit = 1;
+    }
+    lp.kb_per = (lp.kb_total + lp.ksplit - 1) / lp.ksplit;
+    lp.ksplit = (lp.kb_total + lp.kb_per - 1) / lp.kb_per;  // no empty slices
+    lp.a_bytes = kBM * kBK * 4;
+    lp.b_bytes = (unsigned)lp.BN * kBK * 4;
+    lp.stage_bytes = (lp.a_bytes + lp.b_bytes) * (lp.split ? 2 : 1);
+    const size_t tail = 256 + 1024;  // barriers + the TMEM base slot + slack to align the tiles to 1024 bytes
+    lp.stages = (int)(((size_t)smem_optin - tail) / lp.stage_bytes);
+    if (lp.stages > 8) lp.stages = 8;
+    if (lp.stages < 2) return cudaErrorInvalidValue;
+    LinearMaps maps;
+    if (!make_map_2d(&maps.a, A, M, K, kBM) || !make_map_2d(&maps.w, W, N, K, lp.BN)) return cudaErrorInvalidValue;
+    static std::atomic<unsigned long long> done{0};
+    const unsigned long long bit = 1ULL << (device & 63);
+    if (!(done.load(std::memory_order_acquire) & bit)) {
+        cudaError_t e = cudaFuncSetAttribute(linear_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+        if (e != cudaSuccess) return e;
+        done.fetch_or(bit, std::memory_order_release);
+    }
+    const size_t smem = (size_t)lp.stages * lp.stage_bytes + tail;
+    const int tiles = lp.tiles_m * lp.tiles_n * lp.ksplit;
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    if (lp.ksplit > 1) {
+        cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st);
+        if (e != cudaSuccess) return e;
+    }
+    linear_tf32_kernel<<<grid, kThreads, smem, st>>>(bias, C, lp, maps);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace msda

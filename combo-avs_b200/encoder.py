@@ -17,6 +17,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .linear import linear as tc_linear
 from .modules import MSDeformAttn
 
 _ACTIVATIONS = {"relu": F.relu, "gelu": F.gelu, "glu": F.glu}
@@ -48,7 +49,13 @@ class MSDeformAttnTransformerEncoderLayer(nn.Module):
     def with_pos_embed(tensor, pos):
         return tensor if pos is None else tensor + pos
 
+    # the FFN's two GEMMs on the tcgen05 tensor cores at float32 accuracy (combo_avs_b200.linear; ReLU fused into the first epilogue)
+    tensor_core_linear = True
+
     def forward_ffn(self, src):
+        if self.tensor_core_linear and self.activation is F.relu:
+            hidden = self.dropout2(tc_linear(src, self.linear1.weight, self.linear1.bias, relu=True))
+            return self.norm2(src + self.dropout3(tc_linear(hidden, self.linear2.weight, self.linear2.bias)))
         hidden = self.dropout2(self.activation(self.linear1(src)))
         return self.norm2(src + self.dropout3(self.linear2(hidden)))
 

@@ -14,6 +14,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
+from .linear import linear as tc_linear
 from .functions import MSDeformAttnFunction, MSDeformAttnPrologueFunction, _host_geometry, fused_prologue_supported
 
 
@@ -27,6 +28,9 @@ class MSDeformAttn(nn.Module):
     # Fold softmax and the sampling-location arithmetic into the kernels when the call qualifies (CUDA float32, 2-d reference
     # points without gradient, S4-like shapes); same numbers, less memory traffic.  False reproduces the reference's composition.
     fuse_prologue = True
+    # Run the four projections on the tcgen05 tensor cores at float32 accuracy (3xTF32, combo_avs_b200.linear) instead of as
+    # strict-fp32 cuBLAS GEMMs when the call qualifies (CUDA float32, K % 4 == 0, N % 16 == 0).  False: plain nn.Linear.
+    tensor_core_linear = True
 
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         """Multi-scale deformable attention (ms_deform_attn.py:35-66).
@@ -80,9 +84,10 @@ class MSDeformAttn(nn.Module):
         else:
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
-        value = self.value_proj(input_flatten).view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
-        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
-        attention_weights = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
+        proj = (lambda layer, x: tc_linear(x, layer.weight, layer.bias)) if self.tensor_core_linear else (lambda layer, x: layer(x))
+        value = proj(self.value_proj, input_flatten).view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        sampling_offsets = proj(self.sampling_offsets, query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
+        attention_weights = proj(self.attention_weights, query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
         if self.fuse_prologue and fused_prologue_supported(value, input_spatial_shapes, input_level_start_index, reference_points, sampling_offsets) \
@@ -90,7 +95,7 @@ class MSDeformAttn(nn.Module):
             # softmax, location arithmetic and the padding mask happen inside the kernels (include/msda_b200.h: msda_fused_*)
             output = MSDeformAttnPrologueFunction.apply(value, input_spatial_shapes, input_level_start_index, reference_points.contiguous(),
                                                         sampling_offsets, attention_weights, self.im2col_step, input_padding_mask)
-            return self.output_proj(output)
+            return proj(self.output_proj, output)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None, None], float(0))
         attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
@@ -105,4 +110,4 @@ class MSDeformAttn(nn.Module):
         # no try/except here: a failing kernel must be loud (the reference's bare except hides it, ms_deform_attn.py:123)
         output = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
                                             attention_weights.contiguous(), self.im2col_step)
-        return self.output_proj(output)
+        return proj(self.output_proj, output)

@@ -159,6 +159,24 @@ int msda_forward_backward_host(msda_host_pipeline *p, int dtype, int loc_dtype,
                                int N, int S, int M, int D, int L, int Lq, int P, int im2col_step,
                                uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
+/*
+ * Row f2: the Linear layers around the op in the deformable encoder layer -- reference
+ * models/modeling/pixel_decoder/msdeformattn.py:119-134 (linear1 / linear2 of the FFN) and ops/modules/ms_deform_attn.py:105-128
+ * (value_proj, sampling_offsets, attention_weights, output_proj), which the reference runs as strict-fp32 cuBLAS GEMMs.
+ *
+ *   y[M, N] = x[M, K] . weight[N, K]^T + bias[N]            (torch.nn.functional.linear; row-major, float32, 16-byte aligned)
+ *
+ * on the tcgen05 tensor cores with every operand split into two TF32 halves (3 MMAs per product: float32-level accuracy).
+ * Needs K % 4 == 0 and N % 16 == 0 (msda_linear_supported).  The same entry point serves dgrad: pass grad_y as x, weight^T
+ * ([K, N] row-major) as weight, NULL bias -- and wgrad: grad_weight[N, K] = linear(grad_y^T [N, M], x^T [K, M]), where the long
+ * reduction over M is split over the SMs (partial tiles are added into a zeroed result).  flags: MSDA_LINEAR_RELU fuses max(., 0); MSDA_LINEAR_TF32_ONLY skips the split
+ * (plain TF32 accuracy, profiling only).
+ */
+#define MSDA_LINEAR_RELU 1
+#define MSDA_LINEAR_TF32_ONLY 2
+int msda_linear_supported(int M, int N, int K);
+int msda_linear_forward(const void *x, const void *weight, const void *bias, void *y, int M, int N, int K, int flags, int device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
