@@ -41,6 +41,8 @@ struct LinearParams {
     int BN;            // columns of C per tile (multiple of 16, <= 256, divides N)
     int stages;
     int split;         // 1: 3xTF32 (float32 accuracy); 0: plain TF32 (profiling / bring-up only)
+    int split_mode;    // how `hi` is formed: 0 = rewritten in place with the 13 low mantissa bits cleared; 1 = the raw float32 tile is fed
+                       // as is (the tensor core ignores those bits) and lo = x - trunc(x); 2 = raw tile, lo = x - round-to-nearest tf32(x)
     int relu;
     int ksplit;        // > 1: the K blocks of a tile are shared out over `ksplit` work items, which ADD their partial sums into a zeroed C
     int kb_total, kb_per;
@@ -91,6 +93,13 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da
 __device__ __forceinline__ void umma_commit(unsigned bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ float rna_tf32(float x)
+{
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
 }
 
 __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16])
@@ -185,7 +194,13 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
             const int buf = lt & 1, use = lt >> 1;
             if (use > 0) mbar_wait(tempty(buf), (unsigned)((use - 1) & 1));  // the epilogue has drained this accumulator
             tc_fence_after();
-            const unsigned tmem_d = tmem_base + buf * 256;
+            // split mode keeps TWO accumulators per tile: the hi*hi products in one, the 2^-11 times smaller cross terms in the other.
+            // The tensor core truncates when it aligns addends to the accumulator, an error proportional to the accumulator's
+            // magnitude and always in the same direction; kept apart, the cross terms are truncated at THEIR magnitude (negligible)
+            // and the large accumulator sees a third of the additions.  The epilogue adds the two in float32.
+            // (two tiles in flight, 256 TMEM columns each: plain TF32 one accumulator of BN <= 256 columns; split: BN <= 128, hi*hi in
+            // columns 0-127 and the cross terms in 128-255)
+            const unsigned tmem_d = tmem_base + buf * 256, tmem_x = tmem_d + 128;
             for (int kb = 0; kb < kblocks; ++kb, ++it) {
                 const int s = it % lp.stages, round = it / lp.stages;
                 mbar_wait(lp.split ? ready(s) : full(s), (unsigned)(round & 1));
@@ -200,8 +215,8 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
                         umma_tf32(tmem_d, dah, dwh, idesc, (kb | k) != 0);
                         if (lp.split) {
                             const unsigned long long dal = umma_desc(a_lo + koff), dwl = umma_desc(w_lo + koff);
-                            umma_tf32(tmem_d, dah, dwl, idesc, 1);
-                            umma_tf32(tmem_d, dal, dwh, idesc, 1);
+                            umma_tf32(tmem_x, dah, dwl, idesc, (kb | k) != 0);
+                            umma_tf32(tmem_x, dal, dwh, idesc, 1);
                         }
                     }
                     umma_commit(empty(s));                       // the stage is free once these MMAs have read it
@@ -235,11 +250,14 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
                         for (int r = 0; r < 4; ++r) {
                             if (i0 + r * 128 >= n16) break;
                             float4 h, l;
-                            h.x = __uint_as_float(__float_as_uint(x[r].x) & 0xffffe000u); l.x = x[r].x - h.x;
-                            h.y = __uint_as_float(__float_as_uint(x[r].y) & 0xffffe000u); l.y = x[r].y - h.y;
-                            h.z = __uint_as_float(__float_as_uint(x[r].z) & 0xffffe000u); l.z = x[r].z - h.z;
-                            h.w = __uint_as_float(__float_as_uint(x[r].w) & 0xffffe000u); l.w = x[r].w - h.w;
-                            hi[i0 + r * 128] = h;   // (the swizzle permutes 16-byte chunks: an element-wise rewrite keeps the layout)
+                            if (lp.split_mode == 2) {
+                                h.x = rna_tf32(x[r].x); h.y = rna_tf32(x[r].y); h.z = rna_tf32(x[r].z); h.w = rna_tf32(x[r].w);
+                            } else {
+                                h.x = __uint_as_float(__float_as_uint(x[r].x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(x[r].y) & 0xffffe000u);
+                                h.z = __uint_as_float(__float_as_uint(x[r].z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(x[r].w) & 0xffffe000u);
+                            }
+                            l.x = x[r].x - h.x; l.y = x[r].y - h.y; l.z = x[r].z - h.z; l.w = x[r].w - h.w;
+                            if (lp.split_mode == 0) hi[i0 + r * 128] = h;   // (the swizzle permutes 16-byte chunks: an element-wise rewrite keeps the layout)
                             lo[i0 + r * 128] = l;
                         }
                     }
@@ -267,6 +285,12 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
             for (int c0 = 0; c0 < lp.BN; c0 += 16) {
                 float v[16];
                 tmem_ld16(taddr + c0, v);
+                if (lp.split) {
+                    float x[16];
+                    tmem_ld16(taddr + 128 + c0, x);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += x[j];
+                }
                 if (row < lp.M) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -306,10 +330,9 @@ bool make_map_2d(CUtensorMap *map, const float *base, int rows, int cols, int bo
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int pick_bn(int N)
+int pick_bn(int N, int limit)
 {
-    static const int bn_max = [] { const char *e = getenv("MSDA_LINEAR_BN_MAX"); const int v = e ? atoi(e) : 256; return v >= 16 && v <= 256 ? v & ~15 : 256; }();  // A/B switch
-    for (int bn = bn_max; bn >= 16; bn -= 16)
+    for (int bn = limit; bn >= 16; bn -= 16)
         if (N % bn == 0) return bn;
     return 0;
 }
@@ -319,7 +342,7 @@ int pick_bn(int N)
 bool linear_supported(int M, int N, int K)
 {
     // K % 4: the row pitch of x / weight must be a multiple of 16 bytes for the tensor maps (the K tail is zero-filled by TMA)
-    return M > 0 && N > 0 && K > 0 && K % 4 == 0 && N % 16 == 0 && pick_bn(N) >= 16 && tma_encode_fn() != nullptr;
+    return M > 0 && N > 0 && K > 0 && K % 4 == 0 && N % 16 == 0 && pick_bn(N, 128) >= 16 && tma_encode_fn() != nullptr;
 }
 
 cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float *C, int M, int N, int K, int relu, int split, int device,
@@ -327,8 +350,12 @@ cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float
 {
     LinearParams lp;
     lp.M = M; lp.N = N; lp.K = K;
-    lp.BN = pick_bn(N);
     lp.split = split ? 1 : 0;
+    lp.BN = pick_bn(N, lp.split ? 128 : 256);
+    // measured on the B200 (profiles/r05_linear_tcgen05.txt): kind::tf32 ignores the 13 low mantissa bits of its operands (truncation),
+    // so the raw float32 tile IS `hi` and only lo = x - trunc(x) has to be written (mode 1); round-to-nearest halves (mode 2) are wrong
+    static const int smode = [] { const char *e = getenv("MSDA_LINEAR_SPLIT_MODE"); const int v = e ? atoi(e) : 1; return v >= 0 && v <= 2 ? v : 1; }();  // A/B switch
+    lp.split_mode = smode;
     lp.relu = relu ? 1 : 0;
     lp.tiles_m = (M + kBM - 1) / kBM;
     lp.tiles_n = N / lp.BN;

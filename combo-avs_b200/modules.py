@@ -7,6 +7,7 @@ wraps the op call in a bare `except:` that silently reroutes ANY failure to the 
 (ms_deform_attn.py:119-125); this module lets errors propagate -- there is no CPU fallback.
 """
 import math
+import os
 import warnings
 
 import torch
@@ -30,7 +31,7 @@ class MSDeformAttn(nn.Module):
     fuse_prologue = True
     # Run the four projections on the tcgen05 tensor cores at float32 accuracy (3xTF32, combo_avs_b200.linear) instead of as
     # strict-fp32 cuBLAS GEMMs when the call qualifies (CUDA float32, K % 4 == 0, N % 16 == 0).  False: plain nn.Linear.
-    tensor_core_linear = True
+    tensor_core_linear = os.environ.get("MSDA_TC_LINEAR", "1") != "0"
 
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         """Multi-scale deformable attention (ms_deform_attn.py:35-66).
