@@ -35,14 +35,14 @@ constexpr int kBK = 32;           // floats per K block = one 128-byte swizzle r
 constexpr int kUmmaK = 8;         // K of one tcgen05.mma.kind::tf32
 constexpr int kThreads = 320;
 constexpr int kSplitWarp0 = 2, kEpiWarp0 = 6;
+constexpr int kStagePitch = 36;   // floats per staged row: 32 columns + 4 of padding (16-byte aligned, conflict-free both ways)
+constexpr int kBiasFloats = 2048;
 
 struct LinearParams {
     int M, N, K;
     int BN;            // columns of C per tile (multiple of 16, <= 256, divides N)
     int stages;
     int split;         // 1: 3xTF32 (float32 accuracy); 0: plain TF32 (profiling / bring-up only)
-    int split_mode;    // how `hi` is formed: 0 = rewritten in place with the 13 low mantissa bits cleared; 1 = the raw float32 tile is fed
-                       // as is (the tensor core ignores those bits) and lo = x - trunc(x); 2 = raw tile, lo = x - round-to-nearest tf32(x)
     int relu;
     int ksplit;        // > 1: the K blocks of a tile are shared out over `ksplit` work items, which ADD their partial sums into a zeroed C
     int kb_total, kb_per;
@@ -95,13 +95,6 @@ __device__ __forceinline__ void umma_commit(unsigned bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ float rna_tf32(float x)
-{
-    unsigned u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
-
 __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16])
 {
     unsigned r[16];
@@ -132,6 +125,11 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
     auto tfull = [&](int b) { return bars + 8 * (3 * lp.stages + b); };
     auto tempty = [&](int b) { return bars + 8 * (3 * lp.stages + 2 + b); };
     unsigned *tmem_slot = reinterpret_cast<unsigned *>(smem_al + lp.stages * lp.stage_bytes + 8 * (3 * lp.stages + 4));
+    float *stage0 = reinterpret_cast<float *>(smem_al + lp.stages * lp.stage_bytes + 256);   // 4 epilogue warps x 32 rows x kStagePitch floats
+    float *sbias = stage0 + 4 * 32 * kStagePitch;                                            // the bias vector, when it fits kBiasFloats
+    const bool have_sbias = bias != nullptr && lp.N <= kBiasFloats;
+    if (have_sbias)
+        for (int i = threadIdx.x; i < lp.N; i += kThreads) sbias[i] = __ldg(bias + i);
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = lp.tiles_m * lp.tiles_n * lp.ksplit;
     // work item t -> (tile row, tile column, K slice): its K blocks are [kb0, kb0 + kblocks)
@@ -249,15 +247,13 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
                             if (i0 + r * 128 >= n16) break;
-                            float4 h, l;
-                            if (lp.split_mode == 2) {
-                                h.x = rna_tf32(x[r].x); h.y = rna_tf32(x[r].y); h.z = rna_tf32(x[r].z); h.w = rna_tf32(x[r].w);
-                            } else {
-                                h.x = __uint_as_float(__float_as_uint(x[r].x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(x[r].y) & 0xffffe000u);
-                                h.z = __uint_as_float(__float_as_uint(x[r].z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(x[r].w) & 0xffffe000u);
-                            }
-                            l.x = x[r].x - h.x; l.y = x[r].y - h.y; l.z = x[r].z - h.z; l.w = x[r].w - h.w;
-                            if (lp.split_mode == 0) hi[i0 + r * 128] = h;   // (the swizzle permutes 16-byte chunks: an element-wise rewrite keeps the layout)
+                            // kind::tf32 ignores the 13 low mantissa bits of its operands (measured, profiles/r05_linear_tcgen05.txt): the raw
+                            // float32 tile already IS the hi operand; only lo = x - trunc(x) (exact in float32) is written
+                            float4 l;
+                            l.x = x[r].x - __uint_as_float(__float_as_uint(x[r].x) & 0xffffe000u);
+                            l.y = x[r].y - __uint_as_float(__float_as_uint(x[r].y) & 0xffffe000u);
+                            l.z = x[r].z - __uint_as_float(__float_as_uint(x[r].z) & 0xffffe000u);
+                            l.w = x[r].w - __uint_as_float(__float_as_uint(x[r].w) & 0xffffe000u);
                             lo[i0 + r * 128] = l;
                         }
                     }
@@ -268,9 +264,12 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
             }
         }
     } else {
-        // ---- epilogue: TMEM -> registers -> + bias -> global -------------------------------------------------------------------------
+        // ---- epilogue: TMEM -> registers (+ bias, ReLU) -> per-warp staging tile in shared memory -> coalesced global stores ------------
+        // tcgen05.ld hands every lane one ROW of the accumulator; written straight out, a warp store would touch 32 different 128-byte
+        // lines with 16 bytes each (measured: the stores alone then take 143 us for the 41160 x 1024 result, 3.6x the whole rest of the
+        // kernel).  So each warp transposes 32 rows x 32 columns through a padded staging tile and writes 128 contiguous bytes per row.
         const int q = wid & 3;                        // a warp reads the TMEM lanes 32*(warp id % 4) ...
-        const int row_in_tile = q * 32 + lane;
+        float *stage = stage0 + (wid - kEpiWarp0) * (32 * kStagePitch);
         int lt = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++lt) {
             int tm, tn, kb0, kblocks;
@@ -278,32 +277,48 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
             const int buf = lt & 1, use = lt >> 1;
             mbar_wait(tfull(buf), (unsigned)(use & 1));
             tc_fence_after();
-            const int row = tm * kBM + row_in_tile;
-            float *crow = C + (size_t)row * lp.N + tn * lp.BN;
-            const float *brow = (bias && kb0 == 0) ? bias + tn * lp.BN : nullptr;  // (split K: the first slice carries the bias)
+            const int row0 = tm * kBM + q * 32;      // first row of this warp's 32
+            const bool add_bias = bias != nullptr && kb0 == 0;  // (split K: the first slice carries the bias)
             const unsigned taddr = tmem_base + buf * 256 + ((unsigned)(q * 32) << 16);
-            for (int c0 = 0; c0 < lp.BN; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
-                if (lp.split) {
-                    float x[16];
-                    tmem_ld16(taddr + 128 + c0, x);
+            for (int c0 = 0; c0 < lp.BN;) {
+                const int cw = (lp.BN - c0) >= 32 ? 32 : 16;   // columns in this round
+                for (int h = 0; h < cw; h += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0 + h, v);
+                    if (lp.split) {
+                        float x[16];
+                        tmem_ld16(taddr + 128 + c0 + h, x);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += x[j];
-                }
-                if (row < lp.M) {
+                        for (int j = 0; j < 16; ++j) v[j] += x[j];
+                    }
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (brow) {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(brow + c0 + j));
-                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        if (add_bias) {
+                            const float4 bb = have_sbias ? *reinterpret_cast<const float4 *>(sbias + tn * lp.BN + c0 + h + j)
+                                                         : __ldg(reinterpret_cast<const float4 *>(bias + tn * lp.BN + c0 + h + j));
+                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                         }
                         if (lp.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        if (lp.ksplit > 1) red_add_v4(crow + c0 + j, o.x, o.y, o.z, o.w);
-                        else *reinterpret_cast<float4 *>(crow + c0 + j) = o;
+                        *reinterpret_cast<float4 *>(stage + lane * kStagePitch + h + j) = o;
                     }
                 }
+                __syncwarp();
+                const int lpr = cw >> 2, rpi = 32 / lpr;         // lanes per row, rows per store instruction
+                const int rr = lane / lpr, cc = lane - rr * lpr;
+                {
+                    for (int r = rr; r < 32; r += rpi) {
+                        const float4 o = *reinterpret_cast<const float4 *>(stage + r * kStagePitch + cc * 4);
+                        const int row = row0 + r;
+                        if (row < lp.M) {
+                            float *dst = C + (size_t)row * lp.N + tn * lp.BN + c0 + cc * 4;
+                            if (lp.ksplit > 1) red_add_v4(dst, o.x, o.y, o.z, o.w);
+                            else *reinterpret_cast<float4 *>(dst) = o;
+                        }
+                    }
+                }
+                __syncwarp();
+                c0 += cw;
             }
             tc_fence_before();
             __syncwarp();
@@ -351,11 +366,9 @@ cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float
     LinearParams lp;
     lp.M = M; lp.N = N; lp.K = K;
     lp.split = split ? 1 : 0;
+    // split: BN <= 128 so that a tile's two accumulators take 256 TMEM columns and two tiles are in flight (BN = 256 with one tile in
+    // flight measured slower: 184 vs 167 us on 41160 x 1024 x 256, profiles/r05_linear_tcgen05.txt)
     lp.BN = pick_bn(N, lp.split ? 128 : 256);
-    // measured on the B200 (profiles/r05_linear_tcgen05.txt): kind::tf32 ignores the 13 low mantissa bits of its operands (truncation),
-    // so the raw float32 tile IS `hi` and only lo = x - trunc(x) has to be written (mode 1); round-to-nearest halves (mode 2) are wrong
-    static const int smode = [] { const char *e = getenv("MSDA_LINEAR_SPLIT_MODE"); const int v = e ? atoi(e) : 1; return v >= 0 && v <= 2 ? v : 1; }();  // A/B switch
-    lp.split_mode = smode;
     lp.relu = relu ? 1 : 0;
     lp.tiles_m = (M + kBM - 1) / kBM;
     lp.tiles_n = N / lp.BN;
@@ -373,7 +386,8 @@ cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float
     lp.a_bytes = kBM * kBK * 4;
     lp.b_bytes = (unsigned)lp.BN * kBK * 4;
     lp.stage_bytes = (lp.a_bytes + lp.b_bytes) * (lp.split ? 2 : 1);
-    const size_t tail = 256 + 1024;  // barriers + the TMEM base slot + slack to align the tiles to 1024 bytes
+    // barriers + the TMEM base slot (256) + epilogue staging + bias table + slack to align the tiles to 1024 bytes
+    const size_t tail = 256 + 4 * 32 * kStagePitch * 4 + kBiasFloats * 4 + 1024;
     lp.stages = (int)(((size_t)smem_optin - tail) / lp.stage_bytes);
     if (lp.stages > 8) lp.stages = 8;
     if (lp.stages < 2) return cudaErrorInvalidValue;
