@@ -30,6 +30,8 @@ EXPORTS = (
     "msda_fused_backward",
     "msda_linear_supported",
     "msda_linear_forward",
+    "msda_linear_wgrad_supported",
+    "msda_linear_wgrad",
 )
 
 _lib = None
@@ -75,6 +77,10 @@ def load():
     lib.msda_linear_supported.restype = i
     lib.msda_linear_forward.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
     lib.msda_linear_forward.restype = i
+    lib.msda_linear_wgrad_supported.argtypes = [i, i, i]
+    lib.msda_linear_wgrad_supported.restype = i
+    lib.msda_linear_wgrad.argtypes = [vp, vp, vp, i, i, i, i, vp]
+    lib.msda_linear_wgrad.restype = i
     lib.msda_host_pipeline_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), i, i, i]
     lib.msda_host_pipeline_create.restype = i
     lib.msda_host_pipeline_destroy.argtypes = [vp]

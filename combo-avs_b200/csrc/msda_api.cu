@@ -374,8 +374,35 @@ int msda_linear_forward(const void *x, const void *weight, const void *bias, voi
     cudaError_t e = guard.enter(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     e = linear_tf32((const float *)x, (const float *)weight, (const float *)bias, (float *)y, M, N, K, flags & MSDA_LINEAR_RELU,
-                    (flags & MSDA_LINEAR_TF32_ONLY) ? 0 : 1, device, di.sm_count, di.smem_optin, (cudaStream_t)stream);
+                    (flags & MSDA_LINEAR_TF32_ONLY) ? 0 : 1, 0, device, di.sm_count, di.smem_optin, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "msda_linear_forward launch");
+    return MSDA_OK;
+}
+
+int msda_linear_wgrad_supported(int M, int N, int K) { return linear_wgrad_supported(M, N, K) ? 1 : 0; }
+
+int msda_linear_wgrad(const void *grad_y, const void *x, void *grad_weight, int M, int N, int K, int device, void *stream)
+{
+    if (M < 0 || N <= 0 || K <= 0) return fail(MSDA_ERR_DIM, "bad dimensions M=%d N=%d K=%d", M, N, K);
+    if (!grad_weight) return fail(MSDA_ERR_NULL, "grad_weight is NULL");
+    DeviceInfo di;
+    int rc = device_info(device, di);
+    if (rc != MSDA_OK) return rc;
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (M == 0) {  // no rows: the gradient is zero
+        e = cudaMemsetAsync(grad_weight, 0, (size_t)N * K * sizeof(float), (cudaStream_t)stream);
+        return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "cudaMemsetAsync(grad_weight)");
+    }
+    if (!grad_y || !x) return fail(MSDA_ERR_NULL, "NULL pointer in msda_linear_wgrad");
+    if (!linear_wgrad_supported(M, N, K))
+        return fail(MSDA_ERR_VARIANT, "msda_linear_wgrad needs N %% 4 == 0, K %% 32 == 0 and a driver with cuTensorMapEncodeTiled (M=%d N=%d K=%d)", M, N, K);
+    if ((reinterpret_cast<uintptr_t>(grad_y) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(grad_weight)) & 15)
+        return fail(MSDA_ERR_DIM, "msda_linear_wgrad needs 16-byte aligned pointers");
+    e = linear_tf32((const float *)grad_y, (const float *)x, nullptr, (float *)grad_weight, N, K, M, 0, 1, 1, device, di.sm_count, di.smem_optin,
+                    (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "msda_linear_wgrad launch");
     return MSDA_OK;
 }
 

@@ -62,8 +62,9 @@ cudaError_t bwd_sorted32(const Problem &p, const BackwardIO &io, cudaStream_t st
 
 // msda_linear.cu: C[M, N] = A[M, K] . W[N, K]^T + bias on tcgen05 tensor cores (3xTF32 split: float32 accuracy)
 bool linear_supported(int M, int N, int K);
-cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float *C, int M, int N, int K, int relu, int split, int device,
-                        int sm_count, int smem_optin, cudaStream_t st);
+bool linear_wgrad_supported(int M, int N, int K);
+cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float *C, int M, int N, int K, int relu, int split, int mn_major,
+                        int device, int sm_count, int smem_optin, cudaStream_t st);
 
 // zero the rows of grad[rows][row_elems] whose mask byte is set (masked_fill backward, ms_deform_attn.py:103-104)
 cudaError_t zero_masked_rows(float *grad, const unsigned char *mask, long long rows, int row_elems, int sm_count, cudaStream_t st);

@@ -11,13 +11,20 @@
 //
 // Kernel (one persistent CTA per SM, warp-specialised, 320 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled boxes of A [128 x 32] and W [BN x 32] into a ring of stages
-//   warps 2-5   splitters: when a stage has landed, rewrite it in place as `hi` and write `lo` next to it (shared memory only),
-//               fence.proxy.async, hand the stage to
-//   warp 1      the MMA issuer: one elected lane issues 3 x 4 tcgen05.mma (M=128, N=BN, K=8) per stage into one of two TMEM accumulators,
-//               tcgen05.commit releases the stage to the producer and, after the last K block, the accumulator to
-//   warps 6-9   the epilogue: tcgen05.ld the accumulator (lane = row), add the bias (optionally ReLU), store float32 rows;
-//               the other accumulator is being filled meanwhile.
-// C[M, N] = A[M, K] . W[N, K]^T + bias[N]; the same kernel serves the forward (W = weight) and dgrad (W = weight^T, no bias).
+//   warps 2-5   splitters: when a stage has landed, write lo = x - trunc_tf32(x) next to it (shared memory only; kind::tf32 ignores the
+//               13 low mantissa bits of its operands -- measured -- so the raw tile already is `hi`), fence.proxy.async, hand the stage to
+//   warp 1      the MMA issuer: one elected lane issues 3 x 4 tcgen05.mma (M=128, N=BN<=128, K=8) per stage -- hi*hi into one TMEM
+//               accumulator, hi*lo + lo*hi into a second one (the tensor core truncates when it aligns addends; kept apart, the small
+//               cross terms are truncated at their own magnitude and the large accumulator sees a third of the additions);
+//               tcgen05.commit releases the stage to the producer and, after the last K block, the accumulators to
+//   warps 6-9   the epilogue: tcgen05.ld both accumulators (lane = row), add them, the bias (from shared memory) and optionally ReLU or a
+//               ReLU' mask, transpose 32 x 32 blocks through a padded staging tile and write 128 contiguous bytes per row (a direct
+//               row store touches 32 lines with 16 bytes each: measured 143 us for the stores alone); the next tile's accumulators
+//               (the other 256 TMEM columns) are being filled meanwhile.
+// C[M, N] = A[M, K] . W[N, K]^T + bias[N] serves the forward (W = weight) and dgrad (A = grad_y, W = weight^T).  The weight gradient
+// C[N, K] = grad_y[M, N]^T . x[M, K] contracts over the ROWS of both operands: the same kernel in MN-major mode (32 x 32 TMA boxes,
+// transposed-operand bits in the instruction descriptor) reads grad_y and x as they lie in memory, and splits the long contraction over
+// the SMs (partial tiles are added into the zeroed result with red.global.add.v4.f32).
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -44,6 +51,7 @@ struct LinearParams {
     int stages;
     int split;         // 1: 3xTF32 (float32 accuracy); 0: plain TF32 (profiling / bring-up only)
     int relu;
+    int mn_major;      // 1: C[N, K] = A[Mr, N]^T . W[Mr, K] -- both operands are read transposed (MN-major), the contraction runs over their rows
     int ksplit;        // > 1: the K blocks of a tile are shared out over `ksplit` work items, which ADD their partial sums into a zeroed C
     int kb_total, kb_per;
     int tiles_m, tiles_n;
@@ -78,9 +86,26 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr)
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-__device__ __forceinline__ unsigned umma_idesc(int m, int n)
+// (bit 15 / 16: A / B is MN-major, i.e. stored transposed)
+__device__ __forceinline__ unsigned umma_idesc(int m, int n, int mn_major)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(mn_major ? 3 : 0) << 15) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+
+// MN-major operand tile made of 32 (K) x 32 (MN) float boxes, 4096 bytes each, one after the other along MN.  For 32-bit MN-major
+// operands the tensor core accepts exactly one shared-memory layout (cutlass sm100_common.inl:92): the 128-byte swizzle with a 32-byte
+// base -- TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, descriptor layout type 1, cute Swizzle<2,5,2> o ((8,n),(4,k)):((1,LBO),(8,SBO)) in
+// 16-byte units: an atom is 4 K-rows x 32 MN-floats = 512 bytes.  So LBO = 4096 bytes between MN atoms (the next box), SBO = 512 bytes
+// between K atoms (the next four rows of the box), and one K = 8 step advances the start address by 1024 bytes.
+__device__ __forceinline__ unsigned long long umma_desc_mn(unsigned smem_addr)
+{
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr & 0x3ffff) >> 4);
+    d |= (unsigned long long)(4096 >> 4) << 16;
+    d |= (unsigned long long)(512 >> 4) << 32;
+    d |= 1ULL << 46;
+    d |= 1ULL << 61;
+    return d;
 }
 
 __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate)
@@ -177,14 +202,19 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
                     if (round > 0) mbar_wait(empty(s), (unsigned)((round - 1) & 1));
                     const unsigned base = smem_s + s * lp.stage_bytes;
                     mbar_arrive_expect_tx(full(s), lp.a_bytes + lp.b_bytes);
-                    tma_load_2d(base, &maps.a, full(s), (kb0 + kb) * kBK, tm * kBM);       // (columns past K arrive as zeros)
-                    tma_load_2d(base + lp.a_bytes, &maps.w, full(s), (kb0 + kb) * kBK, tn * lp.BN);
+                    if (lp.mn_major) {  // 32 x 32 boxes: 32 rows of the contraction, 32 columns of the operand (rows / columns past the end arrive as zeros)
+                        for (int j = 0; j < kBM / 32; ++j) tma_load_2d(base + j * 4096, &maps.a, full(s), tm * kBM + j * 32, (kb0 + kb) * kBK);
+                        for (int j = 0; j < lp.BN / 32; ++j) tma_load_2d(base + lp.a_bytes + j * 4096, &maps.w, full(s), tn * lp.BN + j * 32, (kb0 + kb) * kBK);
+                    } else {
+                        tma_load_2d(base, &maps.a, full(s), (kb0 + kb) * kBK, tm * kBM);       // (columns past K arrive as zeros)
+                        tma_load_2d(base + lp.a_bytes, &maps.w, full(s), (kb0 + kb) * kBK, tn * lp.BN);
+                    }
                 }
             }
         }
     } else if (wid == 1) {
         // ---- MMA issuer -----------------------------------------------------------------------------------------------------
-        const unsigned idesc = umma_idesc(kBM, lp.BN);
+        const unsigned idesc = umma_idesc(kBM, lp.BN, lp.mn_major);
         int it = 0, lt = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++lt) {
             int tm, tn, kb0, kblocks;
@@ -208,11 +238,14 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
                     const unsigned a_lo = w_hi + lp.b_bytes, w_lo = a_lo + lp.a_bytes;
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const unsigned koff = k * kUmmaK * 4;  // bytes along the swizzled 128-byte row
-                        const unsigned long long dah = umma_desc(a_hi + koff), dwh = umma_desc(w_hi + koff);
+                        // K-major: 32 bytes along the swizzled 128-byte row; MN-major: the next 8-row swizzle atom
+                        const unsigned koff = lp.mn_major ? k * 1024 : k * kUmmaK * 4;
+                        const unsigned long long dah = lp.mn_major ? umma_desc_mn(a_hi + koff) : umma_desc(a_hi + koff);
+                        const unsigned long long dwh = lp.mn_major ? umma_desc_mn(w_hi + koff) : umma_desc(w_hi + koff);
                         umma_tf32(tmem_d, dah, dwh, idesc, (kb | k) != 0);
                         if (lp.split) {
-                            const unsigned long long dal = umma_desc(a_lo + koff), dwl = umma_desc(w_lo + koff);
+                            const unsigned long long dal = lp.mn_major ? umma_desc_mn(a_lo + koff) : umma_desc(a_lo + koff);
+                            const unsigned long long dwl = lp.mn_major ? umma_desc_mn(w_lo + koff) : umma_desc(w_lo + koff);
                             umma_tf32(tmem_x, dah, dwl, idesc, (kb | k) != 0);
                             umma_tf32(tmem_x, dal, dwh, idesc, 1);
                         }
@@ -333,8 +366,9 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
     }
 }
 
-bool make_map_2d(CUtensorMap *map, const float *base, int rows, int cols, int box_rows)
+bool make_map_2d(CUtensorMap *map, const float *base, int rows, int cols, int box_rows, bool mn_major = false)
 {
+    if (box_rows > 256) return false;
     EncodeTiledFn enc = tma_encode_fn();
     if (enc == nullptr || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -342,17 +376,24 @@ bool make_map_2d(CUtensorMap *map, const float *base, int rows, int cols, int bo
     const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-int pick_bn(int N, int limit)
+int pick_bn(int N, int limit, int step = 16)
 {
-    for (int bn = limit; bn >= 16; bn -= 16)
+    for (int bn = limit; bn >= step; bn -= step)
         if (N % bn == 0) return bn;
     return 0;
 }
 
 }  // namespace
+
+// weight-gradient form: C[N, K] = G[M, N]^T . X[M, K] (G, X row-major): N % 4 (row pitch of G), K % 32 (32-column boxes of X)
+bool linear_wgrad_supported(int M, int N, int K)
+{
+    return M > 0 && N > 0 && K > 0 && N % 4 == 0 && K % 32 == 0 && tma_encode_fn() != nullptr;
+}
 
 bool linear_supported(int M, int N, int K)
 {
@@ -360,15 +401,19 @@ bool linear_supported(int M, int N, int K)
     return M > 0 && N > 0 && K > 0 && K % 4 == 0 && N % 16 == 0 && pick_bn(N, 128) >= 16 && tma_encode_fn() != nullptr;
 }
 
-cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float *C, int M, int N, int K, int relu, int split, int device,
-                        int sm_count, int smem_optin, cudaStream_t st)
+// mn_major = 0: C[M, N] = A[M, K] . W[N, K]^T + bias.   mn_major = 1: C[M, N] = A[K, M]^T . W[K, N] (the weight gradient: A = grad_y,
+// W = x, K = their common row count), no bias.
+cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float *C, int M, int N, int K, int relu, int split, int mn_major,
+                        int device, int sm_count, int smem_optin, cudaStream_t st)
 {
     LinearParams lp;
     lp.M = M; lp.N = N; lp.K = K;
     lp.split = split ? 1 : 0;
+    lp.mn_major = mn_major ? 1 : 0;
     // split: BN <= 128 so that a tile's two accumulators take 256 TMEM columns and two tiles are in flight (BN = 256 with one tile in
     // flight measured slower: 184 vs 167 us on 41160 x 1024 x 256, profiles/r05_linear_tcgen05.txt)
-    lp.BN = pick_bn(N, lp.split ? 128 : 256);
+    lp.BN = lp.mn_major ? pick_bn(N, 128, 32) : pick_bn(N, lp.split ? 128 : 256);
+    if (lp.BN < 16) return cudaErrorInvalidValue;
     lp.relu = relu ? 1 : 0;
     lp.tiles_m = (M + kBM - 1) / kBM;
     lp.tiles_n = N / lp.BN;
@@ -392,7 +437,11 @@ cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float
     if (lp.stages > 8) lp.stages = 8;
     if (lp.stages < 2) return cudaErrorInvalidValue;
     LinearMaps maps;
-    if (!make_map_2d(&maps.a, A, M, K, kBM) || !make_map_2d(&maps.w, W, N, K, lp.BN)) return cudaErrorInvalidValue;
+    if (lp.mn_major) {  // operands as they lie in memory: [K rows, M or N columns], fetched in 32 x 32 boxes
+        if (!make_map_2d(&maps.a, A, K, M, 32, true) || !make_map_2d(&maps.w, W, K, N, 32, true)) return cudaErrorInvalidValue;
+    } else if (!make_map_2d(&maps.a, A, M, K, kBM) || !make_map_2d(&maps.w, W, N, K, lp.BN)) {
+        return cudaErrorInvalidValue;
+    }
     static std::atomic<unsigned long long> done{0};
     const unsigned long long bit = 1ULL << (device & 63);
     if (!(done.load(std::memory_order_acquire) & bit)) {

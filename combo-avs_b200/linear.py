@@ -36,6 +36,17 @@ def linear_forward(x2d, weight, bias=None, relu=False, tf32_only=False):
     return y
 
 
+def linear_wgrad(g2d, x2d):
+    """grad_weight[N, K] = g2d[M, N]^T @ x2d[M, K] on the tensor cores, operands read in place (no transposes materialised)."""
+    m, n = g2d.shape
+    k = x2d.shape[1]
+    gw = torch.empty((n, k), dtype=torch.float32, device=g2d.device)
+    dev = g2d.device.index if g2d.device.index is not None else torch.cuda.current_device()
+    rc = _lib.load().msda_linear_wgrad(_ptr(g2d), _ptr(x2d), _ptr(gw), m, n, k, dev, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _lib.check(rc)
+    return gw
+
+
 class TensorCoreLinearFunction(Function):
     """y = [relu](x @ weight^T + bias) with all three GEMMs of the training step on the tensor cores:
     forward, dgrad (grad_x = g @ weight) and wgrad (grad_weight = g^T @ x, its reduction over the rows split over the SMs)."""
@@ -60,9 +71,8 @@ class TensorCoreLinearFunction(Function):
         if ctx.needs_input_grad[0]:  # dgrad: grad_x[M, K] = g[M, N] @ W[N, K] = linear(g, W^T)
             grad_x = linear_forward(g2d, weight.t().contiguous()).view(ctx.x_shape)
         if ctx.needs_input_grad[1]:  # wgrad: grad_W[N, K] = g^T[N, M] @ x[M, K] = linear(g^T, x^T)
-            m = g2d.shape[0]
-            if m % 4 == 0 and weight.shape[1] % 16 == 0:
-                grad_w = linear_forward(g2d.t().contiguous(), x2d.t().contiguous())
+            if _lib.load().msda_linear_wgrad_supported(g2d.shape[0], g2d.shape[1], x2d.shape[1]):
+                grad_w = linear_wgrad(g2d, x2d)
             else:
                 grad_w = g2d.t() @ x2d
         if ctx.has_bias and ctx.needs_input_grad[2]:

@@ -169,13 +169,18 @@ int msda_forward_backward_host(msda_host_pipeline *p, int dtype, int loc_dtype,
  * on the tcgen05 tensor cores with every operand split into two TF32 halves (3 MMAs per product: float32-level accuracy).
  * Needs K % 4 == 0 and N % 16 == 0 (msda_linear_supported).  The same entry point serves dgrad: pass grad_y as x, weight^T
  * ([K, N] row-major) as weight, NULL bias -- and wgrad: grad_weight[N, K] = linear(grad_y^T [N, M], x^T [K, M]), where the long
- * reduction over M is split over the SMs (partial tiles are added into a zeroed result).  flags: MSDA_LINEAR_RELU fuses max(., 0); MSDA_LINEAR_TF32_ONLY skips the split
+ * reduction over M is split over the SMs (partial tiles are added into a zeroed result) -- or, without materialising the
+ * transposes, msda_linear_wgrad below.  flags: MSDA_LINEAR_RELU fuses max(., 0); MSDA_LINEAR_TF32_ONLY skips the split
  * (plain TF32 accuracy, profiling only).
  */
 #define MSDA_LINEAR_RELU 1
 #define MSDA_LINEAR_TF32_ONLY 2
 int msda_linear_supported(int M, int N, int K);
 int msda_linear_forward(const void *x, const void *weight, const void *bias, void *y, int M, int N, int K, int flags, int device, void *stream);
+/* grad_weight[N, K] = grad_y[M, N]^T . x[M, K] (the weight gradient of the same layer), both operands read as they lie in memory
+ * (transposed-operand tcgen05.mma), the contraction over the M rows split over the SMs.  Needs N % 4 == 0 and K % 32 == 0. */
+int msda_linear_wgrad_supported(int M, int N, int K);
+int msda_linear_wgrad(const void *grad_y, const void *x, void *grad_weight, int M, int N, int K, int device, void *stream);
 
 #ifdef __cplusplus
 }

@@ -72,3 +72,29 @@ def test_linear_falls_back_when_it_does_not_apply():
     assert not L.supported(xd, torch.randn(16, 32, device="cuda", dtype=torch.float64))
     with pytest.raises(ValueError):
         L.linear_forward(x, w)
+
+
+def test_linear_wgrad_entry_point_validates_arguments_without_a_gpu():
+    from combo_avs_b200 import _lib
+    L = _lib.load()
+    null = None
+    assert L.msda_linear_wgrad(null, null, null, -1, 16, 32, 0, null) == -2       # bad dimension
+    assert L.msda_linear_wgrad(null, null, null, 4, 16, 32, 0, null) == -1        # NULL result
+    assert L.msda_linear_wgrad_supported(0, 16, 32) == 0
+    assert L.msda_linear_wgrad_supported(64, 18, 32) == 0                         # N % 4
+    assert L.msda_linear_wgrad_supported(64, 16, 48) == 0                         # K % 32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K", [(64, 32, 32), (159, 32, 256), (1029, 100, 96), (5145, 1024, 256), (5145, 256, 1024), (5145, 96, 256)])
+def test_linear_wgrad_matches_float64(M, N, K):
+    """grad_weight[N, K] = grad_y[M, N]^T . x[M, K] with both operands read in place (MN-major tcgen05 operands, 32 x 32 TMA boxes,
+    rows past M zero-filled by TMA), the contraction split over the SMs."""
+    from combo_avs_b200 import linear as L
+    g = torch.Generator().manual_seed(M + N + K)
+    gy = torch.randn(M, N, generator=g).cuda()
+    x = torch.randn(M, K, generator=g).cuda()
+    gw = L.linear_wgrad(gy, x)
+    ref = gy.double().t() @ x.double()
+    err = float((gw.double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err

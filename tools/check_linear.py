@@ -55,6 +55,23 @@ for (M, N, K, relu) in [(128, 256, 32, False), (128, 16, 32, False), (200, 96, 6
         fl = 2.0 * M * N * K
         line += "   ours %.1f us (%.0f TFLOP/s)  cuBLAS fp32 %.1f us  cuBLAS TF32 %.1f us" % (t_ours, fl / t_ours / 1e6, t_cublas, t_tf32)
     print(line, flush=True)
+# the weight gradient with both operands read in place (MN-major): grad_w[N, K] = g[M, N]^T @ x[M, K]
+for (M, N, K) in [(64, 32, 32), (159, 32, 256), (1029, 64, 32), (1029, 100, 96), (41160, 1024, 256), (41160, 256, 1024), (41160, 192, 256), (41160, 96, 256)]:
+    gen = torch.Generator().manual_seed(M + N + K)
+    gy = torch.randn(M, N, generator=gen).to(dev)
+    x = torch.randn(M, K, generator=gen).to(dev)
+    gw = L.linear_wgrad(gy, x)
+    torch.cuda.synchronize()
+    ref = gy.double().t() @ x.double()
+    err = float((gw.double() - ref).abs().max() / ref.abs().max())
+    err_cublas = float(((gy.t() @ x).double() - ref).abs().max() / ref.abs().max())
+    good = err < 2e-5
+    ok &= good
+    line = "wgrad M=%6d N=%4d K=%4d  rel err %.2e (cuBLAS fp32 %.2e) %s" % (M, N, K, err, err_cublas, "ok" if good else "MISMATCH")
+    if M > 40000:
+        line += "   ours %.1f us  cuBLAS fp32 %.1f us" % (timeit(lambda: L.linear_wgrad(gy, x)), timeit(lambda: gy.t() @ x))
+    print(line, flush=True)
+
 # the autograd function against F.linear (forward, grad_x, grad_weight, grad_bias) on an encoder-layer shape
 torch.manual_seed(0)
 for relu in (False, True):
