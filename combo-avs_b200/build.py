@@ -43,6 +43,7 @@ def _compile(src, force, verbose):
            "-ccbin", shutil.which("g++") or "g++", "-c", os.path.join(CSRC, src), "-o", obj + ".tmp"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    cmd[1:1] = os.environ.get("MSDA_NVCC_FLAGS", "").split()  # (tools: A/B builds with experiment macros)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode == 0:
         os.replace(obj + ".tmp", obj)

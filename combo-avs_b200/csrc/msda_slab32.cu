@@ -467,10 +467,6 @@ fwd_slab32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, cons
 // (Round 2 also built the backward's grad_sampling_loc / grad_attn_weight as a second mode of this kernel -- a by-query gather next
 // to a grad_value-only sort-and-segment kernel.  Parity-green, but 110 + 132 us against 206 us for msda_sorted32.cu, which does
 // both in one walk with fewer instructions in total: removed again, measurements in profiles/r04_split_backward_experiments.txt.)
-struct alignas(64) TmaMaps {
-    CUtensorMap level[4];
-};
-constexpr int kTmaMaxLevels = 4;
 constexpr int kFwdTmaThreads = 512;  // including the producer warp
 
 template <int P_T>
@@ -514,7 +510,8 @@ slab32_tma_kernel(const float *__restrict__ loc, const float *__restrict__ attn,
                     if (it > 0) mbar_wait(bars + 8 * (kTmaMaxLevels + l), (unsigned)((it - 1) & 1));  // consumers are past level l of the previous slab
                     const unsigned bytes = (unsigned)((sp.H[l] + 2) * (sp.W[l] + 2)) * kRowBytes;
                     mbar_arrive_expect_tx(bars + 8 * l, bytes);
-                    tma_load_5d(slab_s + (unsigned)sp.prow0[l] * kRowBytes, &maps.level[l], bars + 8 * l, 0, m, -1, -1, n);
+                    // (L2 evict-first: a slab is read by one or two CTAs and never again -- DRAM reads 116 -> 105 MB, profiles/r08a)
+                    tma_load_5d_hint(slab_s + (unsigned)sp.prow0[l] * kRowBytes, &maps.level[l], bars + 8 * l, 0, m, -1, -1, n, l2_policy_evict_first());
                 }
             }
         }

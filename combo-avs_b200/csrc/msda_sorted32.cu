@@ -10,23 +10,24 @@
 //   - the four value rows of the current cell live in registers (loaded once per cell, not once per sample),
 //   - grad_value for the four rows accumulates in registers and leaves with ONE vector reduction per row per cell
 //     visit (about 1.5 M row reductions instead of 15.8 M),
-//   - per sample only ONE 128-byte row is read: its grad_output row, streamed from L2 and prefetched one sample ahead
-//     (the value level slab, zero-padded, sits in shared memory so a cell switch costs 8 LDS, not 8 L2 round trips),
-//   - grad_sampling_loc / grad_attn_weight are 4-lane shuffle reductions and plain stores.
-// MODE bit 0 (default on): the grad_out chunks do not travel through prefetch registers -- ptxas puts all of those LDGs on
-// one scoreboard, so the first use of any of them waits for ALL of them, including the one issued a few instructions
-// earlier (20 % long-scoreboard stalls in profiles/r01p) -- but through a private shared-memory slot per lane, filled by
-// cp.async two steps ahead and read back after cp.async.wait_group 2: a counted, in-order wait.
-// MODE bit 1: the reduction + stores of sample i are deferred into the basic block of sample i+1.
-// Every unit also prefetches the NEXT unit's locations, weights and value rows (and the next slab's grad_out rows) into L2.
-// A lane group is 8 lanes x 4 channels (one 128-byte row per LDS.128 phase: conflict-free); the three per-sample sums
-// are reduced over the 8 lanes with a transposed butterfly (4 shuffles instead of 9).
+//   - per sample only ONE 128-byte row is read: its grad_output row, streamed from L2 and prefetched two samples ahead
+//     into rotating register sets,
+//   - grad_sampling_loc / grad_attn_weight are 8-lane shuffle reductions (transposed butterfly, 4 shuffles) and plain stores.
+// The zero-padded value slab of the level sits in shared memory, so a cell switch costs 4 LDS.128, not 4 L2 round trips.
+// MODE bit 3 (float32 values): the slab is moved by the TMA unit -- ONE cp.async.bulk.tensor issued by one thread per unit, a
+// (H+2) x (W+2) pixel box at (-1, -1) whose out-of-bounds border arrives as zeros, completion on an mbarrier -- instead of
+// eight cp.async + index arithmetic per thread and a hand-zeroed border (profiles/r06a: that staging phase held 16.6 % of the
+// kernel's stall samples, throttled on the load/store queue).
+// A lane group is 8 lanes x 4 channels (one 128-byte row per LDS.128 phase: conflict-free).
+// (The A/B switches of round 1 -- lane splits 2 / 4, a cp.async grad_out ring, a deferred reduction, L2 prefetch of the next
+// unit -- all lost against this configuration and are gone: DESIGN.md section 5.6 keeps their measurements.)
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
 
 #include "msda_kernels.h"
+#include "msda_tma.cuh"
 
 namespace msda {
 namespace {
@@ -47,7 +48,6 @@ struct SortParams {
     int rem;                 // leftover units (units - base*grid), each cut into `parts` pieces: one piece per CTA
     int parts;
     int zero_frames;         // whole units of frames < zero_frames zero their own grad_value slab (the host zeroes the other frames)
-    int prefetch;            // L2-prefetch the next unit's inputs during the walk
     int fused;               // `loc` holds raw offsets: location = ref + offset / (W, H); grad_loc is then d/d(offset)
 };
 
@@ -88,8 +88,6 @@ __device__ __forceinline__ float4 lds4(unsigned addr)
     return v;
 }
 
-__host__ __device__ constexpr int threads_for_split(int split) { return split == 8 ? 768 : split == 4 ? 512 : 384; }
-
 using bf16 = __nv_bfloat16;
 __device__ __forceinline__ float4 load4(const float *p) { return ldg4(p); }
 __device__ __forceinline__ float4 load4(const bf16 *p)
@@ -108,61 +106,236 @@ __device__ __forceinline__ void store1(bf16 *p, float v) { *p = __float2bfloat16
 __device__ __forceinline__ void store2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
 __device__ __forceinline__ void store2(bf16 *p, float a, float b) { *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(a, b); }
 
-// SPLIT lanes share one sample; each lane owns CH = 8/SPLIT chunks of 4 channels.
+// A sample is shared by 8 lanes; each lane owns one chunk of 4 channels.
 // TV: value / grad_out element type (float or bf16; grad_value always accumulates in fp32: for bf16 into a workspace that a
 // second kernel narrows).  TM: element type of sampling locations, attention weights and their gradients.
-template <typename TV, typename TM, int P_T, int SPLIT, int MODE>
-__global__ void __launch_bounds__(threads_for_split(SPLIT), 1)
+// MODE: kModeFused (4) = module prologue folded in; kModeTma (8) = the slab is staged by the TMA unit (float32 values only).
+constexpr int kModeFused = 4, kModeTma = 8;
+constexpr int kSplit = 8, kThreads = 768;
+
+// The walk of one lane over its group's entry range [e_lo, e_hi) of the sorted list.  Everything the loop needs arrives in one
+// struct, so that what the kernel around it keeps alive (unit decode, TMA issue, sort passes) is visibly separate from the loop's
+// own state: ptxas is capped at 80 registers by the 768-thread CTA, and values that leak into the loop cost issue slots there.
+struct WalkArgs {
+    unsigned ent_s, cinfo_s, V_s;  // shared-memory byte addresses: sorted entries, per-cell table, value slab (+ this lane's chunk)
+    int Wpb;                       // bytes per row of the padded slab
+    int e_lo, e_hi, full;          // this group's entries; `full` = entries every group owns (the others own one more)
+    const void *gobase;            // grad_out row 0 of this (frame, head), this lane's chunk
+    unsigned grow_b;               // bytes between grad_out rows of consecutive queries
+    float *gbase;                  // grad_value pixel (0, 0) of this (frame, head, level), this lane's chunk
+    int o01, o10;                  // grad_value element offsets of the right / lower neighbour
+    void *res_base;                // where this lane's result of a sample goes (grad_attn, grad_loc.y or grad_loc.x; lanes 3..7: unused)
+    int res_stride;
+    float res_scale;
+    int qs, j;                     // samples between consecutive queries of one head; lane index inside the group
+};
+
+template <typename TV, typename TM>
+__device__ __forceinline__ void walk_range(const WalkArgs &wa)
+{
+    const unsigned ent_s = wa.ent_s, cinfo_s = wa.cinfo_s, V_s = wa.V_s;
+    const int Wpb = wa.Wpb, e_lo = wa.e_lo, e_hi = wa.e_hi, qs = wa.qs, j = wa.j;
+    const TV *gobase = reinterpret_cast<const TV *>(wa.gobase);
+    const unsigned grow_b = wa.grow_b;
+    float *gbase = wa.gbase;
+    const int o01 = wa.o01, o10 = wa.o10, o11 = wa.o01 + wa.o10;
+    TM *res_base = reinterpret_cast<TM *>(wa.res_base);
+    const int res_stride = wa.res_stride;
+    const float res_scale = wa.res_scale;
+    int cur = -1, inmask = 0;
+    float *gp = gbase;             // grad_value row (this lane's chunk) of the current cell's top-left neighbour
+    f4p v00, dW, dH, dd;           // V00, V01-V00, V10-V00, V11-V10-V01+V00 of the current cell
+    // grad_value of the current cell in the basis (1, lw, lh, lh*lw): sums of att * basis * grad_out
+    const float2 z2 = make_float2(0.f, 0.f);
+    f4p a00 = {z2, z2}, a01 = {z2, z2}, a10 = {z2, z2}, a11 = {z2, z2};
+
+    // (S0, S1, S2, S3) -> the four bilinear weights, one vector reduction per neighbour row inside the map
+    auto flush = [&]() {
+        const f4p r10 = psub(a10, a11);                    // lh*(1-lw)
+        const f4p r00 = psub(psub(a00, a01), r10);         // (1-lh)*(1-lw) = S0 - S1 - (S2 - S3)
+        const f4p r01 = psub(a01, a11);                    // (1-lh)*lw
+        if (inmask == 15) {  // interior cell (86 % of a 28 x 28 level): no predicates, no reconvergence points
+            red_add_v4(gp, r00.lo.x, r00.lo.y, r00.hi.x, r00.hi.y);
+            red_add_v4(gp + o01, r01.lo.x, r01.lo.y, r01.hi.x, r01.hi.y);
+            red_add_v4(gp + o10, r10.lo.x, r10.lo.y, r10.hi.x, r10.hi.y);
+            red_add_v4(gp + o11, a11.lo.x, a11.lo.y, a11.hi.x, a11.hi.y);
+        } else {
+            red_add_v4_if(inmask & 1, gp, r00.lo.x, r00.lo.y, r00.hi.x, r00.hi.y);
+            red_add_v4_if(inmask & 2, gp + o01, r01.lo.x, r01.lo.y, r01.hi.x, r01.hi.y);
+            red_add_v4_if(inmask & 4, gp + o10, r10.lo.x, r10.lo.y, r10.hi.x, r10.hi.y);
+            red_add_v4_if(inmask & 8, gp + o11, a11.lo.x, a11.lo.y, a11.hi.x, a11.hi.y);
+        }
+    };
+    // start the load of the grad_out chunk of sorted entry e2 into the register set g
+    auto issue_g = [&](int e2, float4 &g) {
+        unsigned packed;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(ent_s + e2 * 16 + 12));
+        // 64-bit base + unsigned 32-bit byte offset: two adds instead of a sign-extended 64-bit multiply-shift chain
+        const TV *gq = reinterpret_cast<const TV *>(reinterpret_cast<const char *>(gobase) + (packed & 0xffff) * grow_b);
+        g = load4(gq);
+    };
+    // s_h / s_w arrive already multiplied by the sample's attention weight (cuh:126-127), so the tail is one multiply per lane
+    auto finish = [&](float s_a, float s_h, float s_w, int sidx) {  // transposed butterfly + stores
+        float x = (j & 1) ? s_h : s_a;
+        x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1);
+        s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);
+        float keep = (j & 2) ? s_w : x;
+        keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+        if (sidx >= 0 && j < 3) store1(res_base + sidx * res_stride, keep * res_scale);
+    };
+    // One sample: en = its sorted entry, gr = its grad_out chunk (both already in registers).  Fewest FMA-pipe instructions per
+    // sample: four dot products of grad_out with (V00, dW, dH, dd) combined after the horizontal add; grad_value accumulated in the
+    // basis (1, lw, lh, lh*lw) and converted to the four neighbours once per cell at flush.  The first sample of a cell
+    // STARTS the accumulators (no zeroing at the switch: 22 instructions per switch in the previous SASS).
+#define MSDA_SAMPLE_BODY \
+        float s_a = 0.f, s_h = 0.f, s_w = 0.f, att_v = 0.f; \
+        int sidx = 0; \
+        if (active) { \
+            const int packed = __float_as_int(en.w); \
+            const int cell = packed >> 20; \
+            sidx = (packed & 0xffff) * qs + ((packed >> 16) & 0xf); \
+            att_v = en.z; \
+            const float lh = en.x, lw = en.y; \
+            const float a1s = att_v * lw, a2s = att_v * lh, a3s = a2s * lw; \
+            const float2 b0 = make_float2(att_v, att_v), b1 = make_float2(a1s, a1s), b2 = make_float2(a2s, a2s), b3 = make_float2(a3s, a3s); \
+            const f4p g = pk(gr); \
+            const bool cell_same = cell == cur; \
+            if (!cell_same) { \
+                flush(); \
+                cur = cell; \
+                int2 ci; \
+                asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(ci.x), "=r"(ci.y) : "r"(cinfo_s + cell * 8)); \
+                inmask = ci.x & 15; \
+                gp = gbase + ci.y; \
+                const unsigned a = V_s + (unsigned)(ci.x & ~127); \
+                const f4p t00 = pk(lds4(a)), t01 = pk(lds4(a + kD * 4)), t10 = pk(lds4(a + Wpb)), t11 = pk(lds4(a + Wpb + kD * 4)); \
+                v00 = t00; \
+                dW = psub(t01, t00); \
+                dH = psub(t10, t00); \
+                dd = psub(psub(t11, t10), dW); \
+                a00.lo = __fmul2_rn(b0, g.lo); a00.hi = __fmul2_rn(b0, g.hi); \
+                a01.lo = __fmul2_rn(b1, g.lo); a01.hi = __fmul2_rn(b1, g.hi); \
+                a10.lo = __fmul2_rn(b2, g.lo); a10.hi = __fmul2_rn(b2, g.hi); \
+                a11.lo = __fmul2_rn(b3, g.lo); a11.hi = __fmul2_rn(b3, g.hi); \
+            } else { \
+                a00.lo = __ffma2_rn(b0, g.lo, a00.lo); a00.hi = __ffma2_rn(b0, g.hi, a00.hi); \
+                a01.lo = __ffma2_rn(b1, g.lo, a01.lo); a01.hi = __ffma2_rn(b1, g.hi, a01.hi); \
+                a10.lo = __ffma2_rn(b2, g.lo, a10.lo); a10.hi = __ffma2_rn(b2, g.hi, a10.hi); \
+                a11.lo = __ffma2_rn(b3, g.lo, a11.lo); a11.hi = __ffma2_rn(b3, g.hi, a11.hi); \
+            } \
+            const float2 qA = __ffma2_rn(g.hi, v00.hi, __fmul2_rn(g.lo, v00.lo)); \
+            const float2 qB = __ffma2_rn(g.hi, dW.hi, __fmul2_rn(g.lo, dW.lo)); \
+            const float2 qC = __ffma2_rn(g.hi, dH.hi, __fmul2_rn(g.lo, dH.lo)); \
+            const float2 qE = __ffma2_rn(g.hi, dd.hi, __fmul2_rn(g.lo, dd.lo)); \
+            const float A = qA.x + qA.y, B = qB.x + qB.y, C = qC.x + qC.y, E = qE.x + qE.y; \
+            s_w = __fmaf_rn(lh, E, B); \
+            s_h = __fmaf_rn(lw, E, C); \
+            s_a = __fmaf_rn(lh, s_h, __fmaf_rn(lw, B, A)); \
+        } \
+        finish(s_a, s_h * att_v, s_w * att_v, active ? sidx : -1);
+    // nvcc 12.9 crashes on a generic lambda here, hence two plain lambdas sharing one body
+    auto sample_steady = [&](const float4 &en, const float4 &gr) {
+        const bool active = true;  // steady-state steps are active for every group
+        MSDA_SAMPLE_BODY
+    };
+    auto sample_checked = [&](const float4 &en, const float4 &gr, bool active) {
+        MSDA_SAMPLE_BODY
+    };
+#undef MSDA_SAMPLE_BODY
+
+    // software pipeline: grad_out rows are loaded TWO samples ahead into three rotating register sets (the loop is unrolled
+    // by three so the rotation costs no moves); one sample ahead does not cover the L2 latency.  Every group owns `full`
+    // or `full`+1 entries, so the first `full` steps need no activity checks; the remainder is peeled.
+    const int full = wa.full, cnt = e_hi - e_lo;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 g0 = z4, g1 = z4, g2 = z4;
+    if (cnt > 0) {
+        issue_g(e_lo, g0);
+        issue_g(e_lo + 1, g1);
+    }
+    int it = 0;
+    for (; it + 3 <= full; it += 3) {
+        const int e = e_lo + it;
+        issue_g(e + 2, g2);
+        sample_steady(lds4(ent_s + e * 16), g0);
+        issue_g(e + 3, g0);
+        sample_steady(lds4(ent_s + (e + 1) * 16), g1);
+        issue_g(e + 4, g1);
+        sample_steady(lds4(ent_s + (e + 2) * 16), g2);
+    }
+    // 0..3 remaining steps, activity checked.  (The count is the same for the four groups of a warp up to one step; all of them take
+    // part in the shuffles, so the warp runs the largest count.)
+    const int rem = __reduce_max_sync(0xffffffffu, cnt - it);
+    if (rem >= 1) {
+        const int e = e_lo + it;
+        if (cnt > it + 2) issue_g(e + 2, g2);
+        sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g0, e < e_hi);
+    }
+    if (rem >= 2) {
+        const int e = e_lo + it + 1;
+        sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g1, e < e_hi);
+    }
+    if (rem >= 3) {
+        const int e = e_lo + it + 2;
+        sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g2, e < e_hi);
+    }
+    if (cur >= 0) flush();
+}
+
+template <typename TV, typename TM, int P_T, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
 bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, const TM *__restrict__ attn,
                     const TV *__restrict__ grad_out, float *__restrict__ grad_value, TM *__restrict__ grad_loc,
                     TM *__restrict__ grad_attn, const TM *__restrict__ ref, const unsigned char *__restrict__ mask,
-                    const __grid_constant__ SortParams sp)
+                    const __grid_constant__ SortParams sp, const __grid_constant__ TmaMaps maps)
 {
-    constexpr int kThreads = threads_for_split(SPLIT), CH = 8 / SPLIT;
+    constexpr int SPLIT = kSplit;
     constexpr int kGroups = kThreads / SPLIT, kRounds = (kMaxSamples + kThreads - 1) / kThreads;
     constexpr int kCPT = (kMaxCells + kThreads - 1) / kThreads;  // cells scanned per thread
-    extern __shared__ float4 smem4[];
+    constexpr bool FUSED = (MODE & kModeFused) != 0, TMA = (MODE & kModeTma) != 0 && sizeof(TV) == 4;
+    extern __shared__ __align__(128) float4 smem4[];
     const int Lq = sp.Lq, P = P_T > 0 ? P_T : sp.P, EP = Lq * P, LP = sp.L * P;
     float4 *V4 = smem4;                                   // zero-padded value slab of the current level: (H+2) x (W+2) rows
     float4 *ent = smem4 + (size_t)sp.vrows_max * 8;       // sorted samples: {lh, lw, attn, cell<<20 | p<<16 | q}
     int *cell_off = reinterpret_cast<int *>(ent + EP + 4);  // (four spare entries, see the prefetch) kMaxCells + 1 counters -> exclusive offsets
     int *warp_tot = cell_off + kMaxCells + 8;
-    constexpr bool GRING = (MODE & 1) != 0, DEFER = (MODE & 2) != 0, FUSED = (MODE & 4) != 0;
-    // MODE bit 4 (16): fewer FMA-pipe instructions per sample -- four dot products of grad_out with (V00, dW, dH, dd) combined after
-    // the horizontal add, and grad_value accumulated in the basis (1, lw, lh, lh*lw) and converted to the four neighbours at flush
-    constexpr bool LEAN = (MODE & 16) != 0;
-    // GRING: slot (stage, k) of thread t at gring + ((stage*CH + k) * kThreads + t) * 16 bytes, three stages
     // per-cell facts of the current level, filled while the unit is sorted: {value-slab byte offset of the cell's top-left
     // neighbour | 4-bit mask of the neighbours inside the map, grad_value element offset of that neighbour}
     int2 *cinfo = reinterpret_cast<int2 *>(warp_tot + 32);
     unsigned cinfo_s = (unsigned)__cvta_generic_to_shared(cinfo);
     pin(cinfo_s);
-    unsigned gslot_s = (unsigned)__cvta_generic_to_shared(cinfo + kMaxCells) + threadIdx.x * 16;
-    pin(gslot_s);
+    const unsigned vbar = (unsigned)__cvta_generic_to_shared(cinfo + kMaxCells);  // mbarrier: the slab of the current unit has landed
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int grp = tid / SPLIT;
     int j = tid % SPLIT;                                  // lane j of its sample group
     pin(j);
-    // slot k of this lane is chunk j*CH + ((k + grp) % CH): the 8 lanes of an LDS.128 phase then cover all 32 banks
-    int chf[CH];                                          // float offset of slot k inside a 32-channel row
-#pragma unroll
-    for (int k = 0; k < CH; ++k) {
-        chf[k] = (j * CH + ((k + grp) % CH)) * 4;
-        pin(chf[k]);
-    }
+    int chf = j * 4;                                      // float offset of this lane's chunk inside a 32-channel row
+    pin(chf);
     unsigned ent_s = (unsigned)__cvta_generic_to_shared(ent);
     pin(ent_s);
     const int pix = sp.M * kD;
     const int qstride = sp.M * LP;  // samples between consecutive queries of one head
-
-    // schedule: CTA b runs whole units [b*base, (b+1)*base) and then, if it exists, piece b of the leftover units
-    // (leftover unit grid*base + b/parts, entry range part b%parts of `parts`): without the split the CTAs that get
-    // one unit more than the others set the kernel time (960 units over 148 CTAs: 7 vs 6.49).
+    unsigned vphase = 0;
     const int n_mine = sp.base + ((int)blockIdx.x < sp.rem * sp.parts ? 1 : 0);
+    if (TMA && tid == 0) {
+        mbar_init(vbar, 1);
+        mbar_fence_init();
+        for (int l = 0; l < sp.L; ++l) tma_prefetch_map(&maps.level[l]);
+    }
+
+    // schedule: in round ui, CTA b runs whole unit ui*grid + b; then, if it exists, piece b of the leftover units (leftover unit
+    // grid*base + b/parts, entry range part b%parts of `parts`): without the split the CTAs that get one unit more than the others
+    // set the kernel time (960 units over 148 CTAs: 7 vs 6.49).
+    // The rounds are INTERLEAVED over the CTAs (not a contiguous range per CTA) so that at any time the grid works on ~grid/L
+    // consecutive (frame, head) pairs: the three levels of a pair run concurrently on three SMs and share its grad_out rows, its
+    // location / weight lines and the lines of grad_loc / grad_attn through L2 while they are hot.  With contiguous ranges every CTA
+    // had its own pair in flight -- 2 x 148 x 0.7 MB of reusable lines against a 126 MB L2 that is also streaming 220 MB -- and
+    // DRAM moved 342 MB per launch for 221 MB of algorithmic traffic; interleaved: 179 MB, and 198 -> 178 us (profiles/r08b).
     for (int ui = 0; ui < n_mine; ++ui) {
         const bool piece = ui == sp.base;
         // (32-bit unit arithmetic: every thread decodes its unit, and 64-bit divisions are ~100 instructions each)
-        const int u = piece ? (int)gridDim.x * sp.base + (int)blockIdx.x / sp.parts : (int)blockIdx.x * sp.base + ui;
+        const int u = piece ? (int)gridDim.x * sp.base + (int)blockIdx.x / sp.parts : ui * (int)gridDim.x + (int)blockIdx.x;
         const int part = piece ? (int)blockIdx.x % sp.parts : 0, parts = piece ? sp.parts : 1;
         const int nm = u / sp.L;
         const int l = u - nm * sp.L;
@@ -172,7 +345,14 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         const float Hf = (float)H, Wf = (float)W;
         const long long lvl_row = (n * sp.S + sp.start[l]) * (long long)pix + (long long)m * kD;  // pixel (0,0), channel 0
         const TV *vbase = value + lvl_row;
+        if (TMA && FUSED && mask != nullptr) fence_proxy_async();  // the masked rows zeroed below (generic proxy) precede the next TMA fill
         __syncthreads();  // previous unit is completely finished with V / ent / cell_off
+        if (TMA && tid == 0) {  // one instruction moves the level; the border of the box lies outside the tensor and arrives as zeros
+            mbar_arrive_expect_tx(vbar, (unsigned)((H + 2) * Wp) * (kD * 4));
+            // (L2 evict-first: the level is read once, while grad_out rows, locations and the grad_value lines under reduction are
+            // re-used from L2 for as long as the (frame, head) is worked on -- 200.6 -> 194.8 us, profiles/r08a)
+            tma_load_5d_hint((unsigned)__cvta_generic_to_shared(V4), &maps.level[l], vbar, 0, m, -1, -1, (int)n, l2_policy_evict_first());
+        }
         // ---- pass 1: cell of every sample of this level, rank inside the cell (shared-memory integer atomics) ----------
         // sample (q, p) of this (n, m, l) sits at loc2[q*qstride + p]; per-unit base pointers keep the index math 32-bit
         const long long meta0 = ((n * Lq) * sp.M + m) * (long long)LP + l * P;
@@ -202,30 +382,22 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
             }
         }
         // (the slab copy and the zero fills below overlap the latency of the loads just issued)
-        // value level slab -> shared memory (interior by cp.async, the one-pixel border zeroed by hand)
-        if (sizeof(TV) == 4) {
-            for (int i = tid; i < H * W * 8; i += kThreads) {
-                const int pxl = i >> 3, c = i & 7;
-                const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
-                cp_async16(V4 + ((y + 1) * Wp + x + 1) * 8 + c, vbase + pxl * pix + c * 4);
+        if (!TMA) {
+            // value level slab -> shared memory (interior by cp.async, the one-pixel border zeroed by hand)
+            if (sizeof(TV) == 4) {
+                for (int i = tid; i < H * W * 8; i += kThreads) {
+                    const int pxl = i >> 3, c = i & 7;
+                    const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
+                    cp_async16(V4 + ((y + 1) * Wp + x + 1) * 8 + c, vbase + pxl * pix + c * 4);
+                }
+            } else {  // bf16 rows (64 bytes) are widened to fp32 on the way in
+                for (int i = tid; i < H * W * 8; i += kThreads) {
+                    const int pxl = i >> 3, c = i & 7;
+                    const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
+                    V4[((y + 1) * Wp + x + 1) * 8 + c] = load4(vbase + pxl * pix + c * 4);
+                }
             }
-        } else {  // bf16 rows (64 bytes) are widened to fp32 on the way in
-            for (int i = tid; i < H * W * 8; i += kThreads) {
-                const int pxl = i >> 3, c = i & 7;
-                const int y = (int)__umulhi((unsigned)pxl, sp.wrecip[l]), x = pxl - y * W;
-                V4[((y + 1) * Wp + x + 1) * 8 + c] = load4(vbase + pxl * pix + c * 4);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        // A unit this CTA owns alone zeroes its own slab of grad_value here, right before it accumulates into it: the lines are
-        // still in L2 when the reductions arrive, and no 42 MB memset runs ahead of the kernel.  (The few leftover units that
-        // several CTAs share lie in the frames >= zero_frames, which the host zeroes with a small memset.)
-        if (!piece && n < sp.zero_frames) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            float *gvl = grad_value + lvl_row;
-            for (int i = tid; i < H * W * 8; i += kThreads) *reinterpret_cast<float4 *>(gvl + (i >> 3) * pix + (i & 7) * 4) = z;
-        }
-        {
+            asm volatile("cp.async.commit_group;" ::: "memory");
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             for (int i = tid; i < Wp * 8; i += kThreads) {  // top and bottom padded rows
                 V4[i] = z;
@@ -235,6 +407,14 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                 const int y = (i >> 4) + 1, side = (i >> 3) & 1, c = i & 7;
                 V4[(y * Wp + side * (W + 1)) * 8 + c] = z;
             }
+        }
+        // A unit this CTA owns alone zeroes its own slab of grad_value here, right before it accumulates into it: the lines are
+        // still in L2 when the reductions arrive, and no 42 MB memset runs ahead of the kernel.  (The few leftover units that
+        // several CTAs share lie in the frames >= zero_frames, which the host zeroes with a small memset.)
+        if (!piece && n < sp.zero_frames) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float *gvl = grad_value + lvl_row;
+            for (int i = tid; i < H * W * 8; i += kThreads) *reinterpret_cast<float4 *>(gvl + (i >> 3) * pix + (i & 7) * 4) = z;
         }
         for (int i = tid; i <= cells; i += kThreads) cell_off[i] = 0;
         for (int c = tid; c < cells; c += kThreads) {
@@ -324,9 +504,14 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                 ent[cell_off[cell] + rank] = make_float4(lh, lw, sa[r], __int_as_float((cell << 20) | (p << 16) | q));
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (TMA) {
+            mbar_wait(vbar, vphase);
+            vphase ^= 1;
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         if (FUSED && mask != nullptr) {  // padding mask folded in: masked pixels read as zero rows (their grad_value is zeroed afterwards)
-            __syncthreads();
+            if (!TMA) __syncthreads();
             const unsigned char *mk = mask + n * sp.S + sp.start[l];
             for (int pxl = tid; pxl < H * W; pxl += kThreads) {
                 if (mk[pxl]) {
@@ -338,28 +523,7 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         }
         __syncthreads();  // sorted list complete, value slab landed
 
-        // ---- L2 prefetch of the next whole unit of this CTA: its locations / weights, its value rows and, when it starts a new
-        // (frame, head) slab, its grad_out rows -- so that the next sort and walk find them in L2 instead of paying HBM latency
-        if (sp.prefetch && ui + 1 < sp.base) {
-            const int u2 = u + 1, nm2 = u2 / sp.L;
-            const int l2 = u2 - nm2 * sp.L;
-            const long long n2 = nm2 / sp.M;
-            const int m2 = nm2 - (int)n2 * sp.M;
-            const long long meta2 = ((n2 * Lq) * sp.M + m2) * (long long)LP + l2 * P;
-            const TM *loc2 = loc + 2 * meta2, *att2 = attn + meta2;
-            for (int q = tid; q < Lq; q += kThreads) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(loc2 + 2 * (q * qstride)));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(att2 + q * qstride));
-            }
-            const TV *v2 = value + (n2 * sp.S + sp.start[l2]) * (long long)pix + (long long)m2 * kD;
-            if (sp.prefetch == 1)
-                for (int i = tid; i < sp.H[l2] * sp.W[l2]; i += kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(v2 + i * pix));
-            if (sp.prefetch == 1 && l2 == 0) {
-                const TV *g2p = grad_out + (n2 * Lq * sp.M + m2) * (long long)kD;
-                for (int q = tid; q < Lq; q += kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(g2p + q * pix));
-            }
-        }
-        // ---- walk the sorted list: every SPLIT-lane group owns a contiguous range of entries -------------------------------
+        // ---- walk the sorted list: every 8-lane group owns a contiguous range of entries ------------------------------------
         const int Etot = cell_off[kMaxCells];
         // a piece takes whole cells (the order INSIDE a cell differs between the CTAs that sort the same unit, the cell offsets do
         // not): its range starts at the first cell whose offset reaches Etot*part/parts
@@ -376,255 +540,31 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
             E0 = part == 0 ? 0 : cell_boundary(Etot * part / parts);
             E = (part + 1 == parts ? Etot : cell_boundary(Etot * (part + 1) / parts)) - E0;
         }
-        const int e_lo = E0 + E * grp / kGroups, e_hi = E0 + E * (grp + 1) / kGroups;  // E <= 4608, grp < 384: fits 32 bits
-        // grad_out row of query q: gobase + q*pix (+ chf[k]); streamed from L2, prefetched one entry ahead
-        const TV *gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD + chf[0];  // (this lane's first chunk folded in)
-        unsigned grow_b = (unsigned)pix * (unsigned)sizeof(TV);  // bytes between the grad_out rows of consecutive queries
-        pin(grow_b);
-        float *gbase = grad_value + lvl_row;
-        const int o01 = pix, o10 = W * pix, o11 = (W + 1) * pix;
-        unsigned V_s = (unsigned)__cvta_generic_to_shared(V4);
-        pin(V_s);
-        int qs = qstride, Wpb = Wp * (kD * 4);
-        pin(qs); pin(Wpb);
-        // result stores: SPLIT >= 4: lane 0 grad_attn, lane 1 grad_loc.y, lane 2 grad_loc.x; SPLIT == 2: lane 0 grad_loc (float2), lane 1 grad_attn
-        TM *res_base = SPLIT >= 4 ? (j == 0 ? gatt : gloc + (j == 1 ? 1 : 0)) : (j == 0 ? gloc : gatt);
-        int res_stride = SPLIT >= 4 ? (j == 0 ? 1 : 2) : (j == 0 ? 2 : 1);
+        // every 8-lane group owns a contiguous range of entries; `full` or `full`+1 each
+        WalkArgs wa;
+        wa.ent_s = ent_s;
+        wa.cinfo_s = cinfo_s;
+        wa.V_s = (unsigned)__cvta_generic_to_shared(V4) + chf * 4;
+        wa.Wpb = Wp * (kD * 4);
+        wa.e_lo = E0 + E * grp / kGroups;  // E <= 4608, grp < 96: fits 32 bits
+        wa.e_hi = E0 + E * (grp + 1) / kGroups;
+        wa.full = E / kGroups;
+        wa.gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD + chf;  // grad_out row of query q: gobase + q*pix (this lane's chunk folded in)
+        wa.grow_b = (unsigned)pix * (unsigned)sizeof(TV);                  // bytes between the grad_out rows of consecutive queries
+        wa.gbase = grad_value + lvl_row + chf;
+        wa.o01 = pix;
+        wa.o10 = W * pix;
+        // result stores: lane 0 grad_attn, lane 1 grad_loc.y, lane 2 grad_loc.x
+        wa.res_base = j == 0 ? (void *)gatt : (void *)(gloc + (j == 1 ? 1 : 0));
+        wa.res_stride = j == 0 ? 1 : 2;
         // d(loc)/d(offset) = 1 / (W, H) cancels the (W, H) factor of grad_sampling_loc (cuh:126-127) in the fused form
-        float res_scale = (j == 0 || FUSED) ? 1.f : (j == 1 ? Hf : Wf);
-        pin(res_base); pin(res_stride); pin(res_scale); pin(gobase); pin(gbase);
-        int cur = -1, inmask = 0;
-        float *gp = gbase;             // grad_value row of the current cell's top-left neighbour
-        f4p v00[CH], dW[CH], dH[CH], dd[CH];       // V00, V01-V00, V10-V00, V11-V10-V01+V00 per owned chunk
-        f4p a00[CH], a01[CH], a10[CH], a11[CH];    // grad_value accumulators of the four neighbour rows
-        const float2 z2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < CH; ++k) a00[k] = a01[k] = a10[k] = a11[k] = {z2, z2};
-
-        auto flush = [&]() {
-#pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                float *gk = gp + chf[k];
-                f4p r00 = a00[k], r01 = a01[k], r10 = a10[k];
-                if (LEAN) {  // (S0, S1, S2, S3) = sums of att * (1, lw, lh, lh*lw) * g  ->  the four bilinear weights (into temporaries:
-                             // the accumulators themselves are only ever zeroed, so no register moves at the branch merge)
-                    r10 = psub(a10[k], a11[k]);                    // lh*(1-lw)
-                    r00 = psub(psub(a00[k], a01[k]), r10);         // (1-lh)*(1-lw) = S0 - S1 - (S2 - S3)
-                    r01 = psub(a01[k], a11[k]);                    // (1-lh)*lw
-                }
-                red_add_v4_if(inmask & 1, gk, r00.lo.x, r00.lo.y, r00.hi.x, r00.hi.y);
-                red_add_v4_if(inmask & 2, gk + o01, r01.lo.x, r01.lo.y, r01.hi.x, r01.hi.y);
-                red_add_v4_if(inmask & 4, gk + o10, r10.lo.x, r10.lo.y, r10.hi.x, r10.hi.y);
-                red_add_v4_if(inmask & 8, gk + o11, a11[k].lo.x, a11[k].lo.y, a11[k].hi.x, a11[k].hi.y);
-            }
-        };
-        // start the loads of the grad_out chunks of sorted entry e2 (clamped to this group's range): into the lane's shared-memory
-        // slot `si` (GRING; one cp.async group per call) or into the register set g
-        auto issue_g = [&](int e2, int si, float4 (&g)[CH]) {
-            unsigned packed;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(ent_s + e2 * 16 + 12));
-            // 64-bit base + unsigned 32-bit byte offset: two adds instead of a sign-extended 64-bit multiply-shift chain
-            const TV *gq = reinterpret_cast<const TV *>(reinterpret_cast<const char *>(gobase) + (packed & 0xffff) * grow_b);
-            if (GRING) {
-#pragma unroll
-                for (int k = 0; k < CH; ++k) {
-                    const unsigned slot = gslot_s + (unsigned)((si * CH + k) * kThreads) * 16;
-                    if (sizeof(TV) == 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(gq + (chf[k] - chf[0])) : "memory");
-                    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(slot), "l"(gq + (chf[k] - chf[0])) : "memory");
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            } else {
-#pragma unroll
-                for (int k = 0; k < CH; ++k) g[k] = load4(gq + (chf[k] - chf[0]));
-            }
-        };
-        // GRING: wait for the copy into slot `si` (all but the two newest groups, or everything when `drain`) and read it back
-        auto fetch_g = [&](int si, bool drain, float4 (&g)[CH]) {
-            if (!GRING) return;
-            if (drain) asm volatile("cp.async.wait_group 0;" ::: "memory");
-            else asm volatile("cp.async.wait_group 2;" ::: "memory");
-#pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const unsigned slot = gslot_s + (unsigned)((si * CH + k) * kThreads) * 16;
-                if (sizeof(TV) == 4) {
-                    g[k] = lds4(slot);
-                } else {
-                    uint2 r;
-                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(slot));
-                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.x));
-                    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&r.y));
-                    g[k] = make_float4(a.x, a.y, b.x, b.y);
-                }
-            }
-        };
-        // deferred tail of the previous sample (DEFER): its three lane-partial sums, weight and result index
-        float d_a = 0.f, d_h = 0.f, d_w = 0.f;
-        int d_idx = -1;
-        // s_h / s_w arrive already multiplied by the sample's attention weight (cuh:126-127), so the tail is one multiply per lane
-        auto finish = [&](float s_a, float s_h, float s_w, int sidx) {  // SPLIT >= 4: transposed butterfly + stores
-            float x = (j & 1) ? s_h : s_a;
-            x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1);
-            s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);
-            float keep = (j & 2) ? s_w : x;
-            keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2);
-            if (SPLIT == 8) keep += __shfl_xor_sync(0xffffffffu, keep, 4);
-            if (sidx >= 0 && j < 3)
-                store1(res_base + sidx * res_stride, keep * res_scale);
-        };
-        // one sample: en = its sorted entry, gr = its grad_out chunks (both already in registers)
-#define MSDA_SAMPLE_BODY \
-            float s_a = 0.f, s_h = 0.f, s_w = 0.f, att_v = 0.f; \
-            int sidx = 0; \
-            if (active) { \
-                const int packed = __float_as_int(en.w); \
-                const int cell = packed >> 20; \
-                sidx = (packed & 0xffff) * qs + ((packed >> 16) & 0xf); \
-                att_v = en.z; \
-                if (cell != cur) { \
-                    flush(); \
-                    cur = cell; \
-                    int2 ci; \
-                    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(ci.x), "=r"(ci.y) : "r"(cinfo_s + cell * 8)); \
-                    inmask = ci.x & 15; \
-                    gp = gbase + ci.y; \
-                    const unsigned vr = V_s + (unsigned)(ci.x & ~127); \
-_Pragma("unroll") \
-                    for (int k = 0; k < CH; ++k) { \
-                        const unsigned a = vr + chf[k] * 4; \
-                        const f4p t00 = pk(lds4(a)), t01 = pk(lds4(a + kD * 4)), t10 = pk(lds4(a + Wpb)), t11 = pk(lds4(a + Wpb + kD * 4)); \
-                        v00[k] = t00; \
-                        dW[k] = psub(t01, t00); \
-                        dH[k] = psub(t10, t00); \
-                        dd[k] = psub(psub(t11, t10), dW[k]); \
-                        a00[k] = a01[k] = a10[k] = a11[k] = {z2, z2}; \
-                    } \
-                } \
-                const float lh = en.x, lw = en.y; \
-                if (LEAN) { \
-                    const float a1s = att_v * lw, a2s = att_v * lh, a3s = a2s * lw; \
-                    const float2 b0 = make_float2(att_v, att_v), b1 = make_float2(a1s, a1s), b2 = make_float2(a2s, a2s), b3 = make_float2(a3s, a3s); \
-                    float2 qA = z2, qB = z2, qC = z2, qE = z2; \
-_Pragma("unroll") \
-                    for (int k = 0; k < CH; ++k) { \
-                        const f4p g = pk(gr[k]); \
-                        qA = __ffma2_rn(g.hi, v00[k].hi, __ffma2_rn(g.lo, v00[k].lo, qA)); \
-                        qB = __ffma2_rn(g.hi, dW[k].hi, __ffma2_rn(g.lo, dW[k].lo, qB)); \
-                        qC = __ffma2_rn(g.hi, dH[k].hi, __ffma2_rn(g.lo, dH[k].lo, qC)); \
-                        qE = __ffma2_rn(g.hi, dd[k].hi, __ffma2_rn(g.lo, dd[k].lo, qE)); \
-                        a00[k].lo = __ffma2_rn(b0, g.lo, a00[k].lo); a00[k].hi = __ffma2_rn(b0, g.hi, a00[k].hi); \
-                        a01[k].lo = __ffma2_rn(b1, g.lo, a01[k].lo); a01[k].hi = __ffma2_rn(b1, g.hi, a01[k].hi); \
-                        a10[k].lo = __ffma2_rn(b2, g.lo, a10[k].lo); a10[k].hi = __ffma2_rn(b2, g.hi, a10[k].hi); \
-                        a11[k].lo = __ffma2_rn(b3, g.lo, a11[k].lo); a11[k].hi = __ffma2_rn(b3, g.hi, a11[k].hi); \
-                    } \
-                    const float A = qA.x + qA.y, B = qB.x + qB.y, C = qC.x + qC.y, E = qE.x + qE.y; \
-                    s_w = __fmaf_rn(lh, E, B); \
-                    s_h = __fmaf_rn(lw, E, C); \
-                    s_a = __fmaf_rn(lh, s_h, __fmaf_rn(lw, B, A)); \
-                } else { \
-                const float ah = (1.f - lh) * att_v, al = lh * att_v, hw = 1.f - lw; \
-                const float2 lh2 = make_float2(lh, lh), lw2 = make_float2(lw, lw); \
-                const float2 w1 = make_float2(ah * hw, ah * hw), w2 = make_float2(ah * lw, ah * lw); \
-                const float2 w3 = make_float2(al * hw, al * hw), w4 = make_float2(al * lw, al * lw); \
-                float2 pa = z2, ph = z2, pw = z2; \
-_Pragma("unroll") \
-                for (int k = 0; k < CH; ++k) { \
-                    const f4p g = pk(gr[k]); \
-                    const float2 dh0 = __ffma2_rn(lw2, dd[k].lo, dH[k].lo), dh1 = __ffma2_rn(lw2, dd[k].hi, dH[k].hi); \
-                    const float2 tp0 = __ffma2_rn(lw2, dW[k].lo, v00[k].lo), tp1 = __ffma2_rn(lw2, dW[k].hi, v00[k].hi); \
-                    const float2 dw0 = __ffma2_rn(lh2, dd[k].lo, dW[k].lo), dw1 = __ffma2_rn(lh2, dd[k].hi, dW[k].hi); \
-                    pa = __ffma2_rn(g.hi, __ffma2_rn(lh2, dh1, tp1), __ffma2_rn(g.lo, __ffma2_rn(lh2, dh0, tp0), pa)); \
-                    ph = __ffma2_rn(g.hi, dh1, __ffma2_rn(g.lo, dh0, ph)); \
-                    pw = __ffma2_rn(g.hi, dw1, __ffma2_rn(g.lo, dw0, pw)); \
-                    a00[k].lo = __ffma2_rn(w1, g.lo, a00[k].lo); a00[k].hi = __ffma2_rn(w1, g.hi, a00[k].hi); \
-                    a01[k].lo = __ffma2_rn(w2, g.lo, a01[k].lo); a01[k].hi = __ffma2_rn(w2, g.hi, a01[k].hi); \
-                    a10[k].lo = __ffma2_rn(w3, g.lo, a10[k].lo); a10[k].hi = __ffma2_rn(w3, g.hi, a10[k].hi); \
-                    a11[k].lo = __ffma2_rn(w4, g.lo, a11[k].lo); a11[k].hi = __ffma2_rn(w4, g.hi, a11[k].hi); \
-                } \
-                s_a = pa.x + pa.y; \
-                s_h = ph.x + ph.y; \
-                s_w = pw.x + pw.y; \
-                } \
-            } \
-            if (SPLIT == 2) { \
-                s_a += __shfl_xor_sync(0xffffffffu, s_a, 1); \
-                s_h += __shfl_xor_sync(0xffffffffu, s_h, 1); \
-                s_w += __shfl_xor_sync(0xffffffffu, s_w, 1); \
-                if (active) { \
-                    if (j == 0) store2(res_base + sidx * 2, (FUSED ? 1.f : Wf) * att_v * s_w, (FUSED ? 1.f : Hf) * att_v * s_h); \
-                    else store1(res_base + sidx, s_a); \
-                } \
-            } else if (DEFER) { \
-                finish(d_a, d_h, d_w, d_idx); \
-                d_a = s_a; d_h = s_h * att_v; d_w = s_w * att_v; d_idx = active ? sidx : -1; \
-            } else { \
-                finish(s_a, s_h * att_v, s_w * att_v, active ? sidx : -1); \
-            }
-        // nvcc 12.9 crashes on a generic lambda here, hence two plain lambdas sharing one body
-        auto sample_steady = [&](const float4 &en, const float4 (&gr)[CH]) {
-            const bool active = true;  // steady-state steps are active for every group
-            MSDA_SAMPLE_BODY
-        };
-        auto sample_checked = [&](const float4 &en, const float4 (&gr)[CH], bool active) {
-            MSDA_SAMPLE_BODY
-        };
-#undef MSDA_SAMPLE_BODY
-
-        // software pipeline: grad_out rows are loaded TWO samples ahead into three rotating register sets (the loop is unrolled
-        // by three so the rotation costs no moves); one sample ahead does not cover the L2 latency.  Every group owns `full`
-        // or `full`+1 entries, so the first `full` steps need no activity checks; the remainder is peeled.
-        const int full = E / kGroups, cnt = e_hi - e_lo;
-        const bool has_tail = full * kGroups != E;
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 g0[CH], g1[CH], g2[CH];
-#pragma unroll
-        for (int k = 0; k < CH; ++k) g0[k] = g1[k] = g2[k] = z4;
-        if (cnt > 0) {
-            issue_g(e_lo, 0, g0);
-            issue_g(e_lo + 1, 1, g1);
-        }
-        int it = 0;
-        for (; it + 3 <= full; it += 3) {
-            const int e = e_lo + it;
-            issue_g(e + 2, 2, g2);
-            fetch_g(0, false, g0);
-            sample_steady(lds4(ent_s + e * 16), g0);
-            issue_g(e + 3, 0, g0);
-            fetch_g(1, false, g1);
-            sample_steady(lds4(ent_s + (e + 1) * 16), g1);
-            issue_g(e + 4, 1, g1);
-            fetch_g(2, false, g2);
-            sample_steady(lds4(ent_s + (e + 2) * 16), g2);
-        }
-        const int rem = full - it + (has_tail ? 1 : 0);  // 0..3 remaining steps, the same for every group
-        if (rem >= 1) {
-            const int e = e_lo + it;
-            if (cnt > 0 && rem >= 3) issue_g(e + 2, 2, g2);
-            fetch_g(0, true, g0);  // (the remainder drains the copy queue: its group count depends on rem)
-            sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g0, e < e_hi);
-        }
-        if (rem >= 2) {
-            const int e = e_lo + it + 1;
-            fetch_g(1, true, g1);
-            sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g1, e < e_hi);
-        }
-        if (rem >= 3) {
-            const int e = e_lo + it + 2;
-            fetch_g(2, true, g2);
-            sample_checked(e < e_hi ? lds4(ent_s + e * 16) : z4, g2, e < e_hi);
-        }
-        if (DEFER && SPLIT >= 4) {
-            finish(d_a, d_h, d_w, d_idx);
-            d_idx = -1;
-        }
-        if (GRING) asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing may land in a slot during the next unit
-        if (cur >= 0) flush();
+        wa.res_scale = (j == 0 || FUSED) ? 1.f : (j == 1 ? Hf : Wf);
+        wa.qs = qstride;
+        wa.j = j;
+        walk_range<TV, TM>(wa);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!TMA) asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
-
-// (the A/B switches of round 1 -- lane splits 2 / 4, the cp.async grad_out ring, the deferred reduction, L2 prefetch -- all lost
-// against this configuration and are no longer instantiated: DESIGN.md section 5.6 keeps their measurements)
-constexpr int kSplit = 8, kModeLean = 16, kModeLeanFused = 20;
 
 bool make_params(const Problem &p, SortParams &sp, size_t &smem)
 {
@@ -650,9 +590,8 @@ bool make_params(const Problem &p, SortParams &sp, size_t &smem)
     }
     sp.units = (long long)p.N * p.M * p.L;
     if (sp.units >= (1LL << 30)) return false;  // 32-bit unit arithmetic in the kernel
-    smem = (size_t)sp.vrows_max * 8 * 16 + ((size_t)p.Lq * p.P + 4) * 16 + (kMaxCells + 8 + 32) * sizeof(int) + kMaxCells * sizeof(int2);
+    smem = (size_t)sp.vrows_max * 8 * 16 + ((size_t)p.Lq * p.P + 4) * 16 + (kMaxCells + 8 + 32) * sizeof(int) + kMaxCells * sizeof(int2) + 16;  // (+ the slab mbarrier)
     if (smem > (size_t)p.smem_optin) return false;
-    sp.prefetch = 0;
     sp.fused = p.ref != nullptr ? 1 : 0;
     if (sp.fused && p.loc_dtype != 0) return false;
     return true;
@@ -668,7 +607,8 @@ template <auto Kern> cudaError_t ensure_smem_optin(const Problem &p)
     return e;
 }
 
-// schedule: `grid` persistent CTAs take `base` whole units each; the `rem` leftover units are cut into `parts` pieces, one per CTA
+// schedule: `grid` persistent CTAs take `base` whole units each (round-robin: unit ui*grid + b); the `rem` leftover units are cut
+// into `parts` pieces, one per CTA
 void plan_units(const Problem &p, SortParams &sp, int &grid)
 {
     grid = (int)(sp.units < p.sm_count ? sp.units : p.sm_count);
@@ -682,25 +622,44 @@ void plan_units(const Problem &p, SortParams &sp, int &grid)
     sp.zero_frames = sp.rem > 0 ? (int)(((long long)grid * sp.base / p.L) / p.M) : p.N;
 }
 
+// Tensor maps of the levels for the TMA staging; false when a level does not fit a box, the pointer is misaligned, the driver
+// lacks cuTensorMapEncodeTiled or MSDA_SORTED_TMA=0 asks for the cp.async staging (A/B switch).
+bool make_level_maps(const Problem &p, const SortParams &sp, TmaMaps &maps)
+{
+    static const bool off = [] { const char *e = getenv("MSDA_SORTED_TMA"); return e && atoi(e) == 0; }();
+    if (off || p.dtype != 0 || p.L > kTmaMaxLevels) return false;
+    for (int l = 0; l < p.L; ++l)
+        if (!tma_make_level_map(&maps.level[l], (const float *)p.value + (size_t)sp.start[l] * p.M * kD, p.N, p.S, p.M, sp.H[l], sp.W[l]))
+            return false;
+    return true;
+}
+
 template <typename TV, typename TM>
 cudaError_t launch_sorted(const Problem &p, const BackwardIO &io, float *gv_acc, SortParams &sp, size_t smem, int grid, cudaStream_t st)
 {
+    TmaMaps maps;
+    bool tma = false;
+    if constexpr (std::is_same<TV, float>::value) tma = make_level_maps(p, sp, maps);
     auto go = [&](auto kern_c) {
         constexpr auto kern = decltype(kern_c)::value;
         cudaError_t e = ensure_smem_optin<kern>(p);
         if (e != cudaSuccess) return e;
-        kern<<<grid, threads_for_split(kSplit), smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (const TV *)io.grad_out, gv_acc,
-                                                          (TM *)io.grad_loc, (TM *)io.grad_attn, (const TM *)p.ref, p.mask, sp);
+        kern<<<grid, kThreads, smem, st>>>((const TV *)p.value, (const TM *)p.loc, (const TM *)p.attn, (const TV *)io.grad_out, gv_acc,
+                                           (TM *)io.grad_loc, (TM *)io.grad_attn, (const TM *)p.ref, p.mask, sp, maps);
         count_launch();
         return cudaGetLastError();
     };
     using std::integral_constant;
-#define MSDA_SORTED_KERN(PT, MD) integral_constant<decltype(&bwd_sorted32_kernel<TV, TM, PT, kSplit, MD>), &bwd_sorted32_kernel<TV, TM, PT, kSplit, MD>>()
-    if constexpr (std::is_same<TV, float>::value && std::is_same<TM, float>::value) {  // the fused prologue is float32-only
-        if (sp.fused) return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeLeanFused)) : go(MSDA_SORTED_KERN(0, kModeLeanFused));
+#define MSDA_SORTED_KERN(PT, MD) integral_constant<decltype(&bwd_sorted32_kernel<TV, TM, PT, MD>), &bwd_sorted32_kernel<TV, TM, PT, MD>>()
+    if constexpr (std::is_same<TV, float>::value && std::is_same<TM, float>::value) {  // the fused prologue and the TMA staging are float32-only
+        if (sp.fused) {
+            if (tma) return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeFused | kModeTma)) : go(MSDA_SORTED_KERN(0, kModeFused | kModeTma));
+            return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeFused)) : go(MSDA_SORTED_KERN(0, kModeFused));
+        }
+        if (tma) return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeTma)) : go(MSDA_SORTED_KERN(0, kModeTma));
     }
     if (sp.fused) return cudaErrorInvalidValue;
-    return p.P == 4 ? go(MSDA_SORTED_KERN(4, kModeLean)) : go(MSDA_SORTED_KERN(0, kModeLean));
+    return p.P == 4 ? go(MSDA_SORTED_KERN(4, 0)) : go(MSDA_SORTED_KERN(0, 0));
 #undef MSDA_SORTED_KERN
 }
 

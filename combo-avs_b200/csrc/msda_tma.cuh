@@ -53,6 +53,12 @@ inline bool tma_make_level_map(CUtensorMap *map, const float *level_base, int N,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// one tensor map per level, handed to the kernels by value (__grid_constant__)
+constexpr int kTmaMaxLevels = 4;
+struct alignas(64) TmaMaps {
+    CUtensorMap level[kTmaMaxLevels];
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
@@ -85,6 +91,27 @@ __device__ __forceinline__ void tma_load_5d(unsigned dst, const CUtensorMap *map
 {
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// the same with an L2 eviction policy (createpolicy) for the global-memory side of the copy
+__device__ __forceinline__ void tma_load_5d_hint(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1, int c2, int c3, int c4,
+                                                 unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy) : "memory");
+}
+// L2 eviction policies: evict_first for data that is read once (a value slab on its way into shared memory), evict_last for data
+// that is re-read from L2 while a unit is processed (grad_output rows)
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ void tma_prefetch_map(const CUtensorMap *map)
 {
