@@ -345,14 +345,13 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         const float Hf = (float)H, Wf = (float)W;
         const long long lvl_row = (n * sp.S + sp.start[l]) * (long long)pix + (long long)m * kD;  // pixel (0,0), channel 0
         const TV *vbase = value + lvl_row;
-        if (TMA && FUSED && mask != nullptr) fence_proxy_async();  // the masked rows zeroed below (generic proxy) precede the next TMA fill
-        __syncthreads();  // previous unit is completely finished with V / ent / cell_off
-        if (TMA && tid == 0) {  // one instruction moves the level; the border of the box lies outside the tensor and arrives as zeros
-            mbar_arrive_expect_tx(vbar, (unsigned)((H + 2) * Wp) * (kD * 4));
-            // (L2 evict-first: the level is read once, while grad_out rows, locations and the grad_value lines under reduction are
-            // re-used from L2 for as long as the (frame, head) is worked on -- 200.6 -> 194.8 us, profiles/r08a)
-            tma_load_5d_hint((unsigned)__cvta_generic_to_shared(V4), &maps.level[l], vbar, 0, m, -1, -1, (int)n, l2_policy_evict_first());
-        }
+        // What does not touch shared memory goes BEFORE the barrier that ends the previous unit: the loads of this unit's locations and
+        // weights (into registers) and the zeroing of its grad_value slab are issued by every warp as soon as IT has finished its part of
+        // the previous walk, so their latency runs under the wait for the slowest group instead of after it (that barrier alone held
+        // 4.5 % of the kernel's stall samples, the location loads' long-scoreboard wait another 4.5 %: profiles/r08c): 177.7 -> 171.7 us.
+        // (Going further -- the per-cell table and the whole counting pass ahead of the barrier too, into a second set of counters --
+        // LOSES: 184 us; the early warps' shared-memory atomics and stores compete with the warps that are still walking, and those
+        // set the time.  profiles/r08a-f_*, profiles/experiments/r08f_*.patch)
         // ---- pass 1: cell of every sample of this level, rank inside the cell (shared-memory integer atomics) ----------
         // sample (q, p) of this (n, m, l) sits at loc2[q*qstride + p]; per-unit base pointers keep the index math 32-bit
         const long long meta0 = ((n * Lq) * sp.M + m) * (long long)LP + l * P;
@@ -381,6 +380,22 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                 sa[r] = load1(att + q * qstride + p);
             }
         }
+        // A unit this CTA owns alone zeroes its own slab of grad_value here, right before it accumulates into it: the lines are
+        // still in L2 when the reductions arrive, and no 42 MB memset runs ahead of the kernel.  (The few leftover units that
+        // several CTAs share lie in the frames >= zero_frames, which the host zeroes with a small memset.)
+        if (!piece && n < sp.zero_frames) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float *gvl = grad_value + lvl_row;
+            for (int i = tid; i < H * W * 8; i += kThreads) *reinterpret_cast<float4 *>(gvl + (i >> 3) * pix + (i & 7) * 4) = z;
+        }
+        if (TMA && FUSED && mask != nullptr) fence_proxy_async();  // the masked rows zeroed below (generic proxy) precede the next TMA fill
+        __syncthreads();  // previous unit is completely finished with V / ent / cell_off
+        if (TMA && tid == 0) {  // one instruction moves the level; the border of the box lies outside the tensor and arrives as zeros
+            mbar_arrive_expect_tx(vbar, (unsigned)((H + 2) * Wp) * (kD * 4));
+            // (L2 evict-first: the level is read once, while grad_out rows, locations and the grad_value lines under reduction are
+            // re-used from L2 for as long as the (frame, head) is worked on -- 200.6 -> 194.8 us, profiles/r08a)
+            tma_load_5d_hint((unsigned)__cvta_generic_to_shared(V4), &maps.level[l], vbar, 0, m, -1, -1, (int)n, l2_policy_evict_first());
+        }
         // (the slab copy and the zero fills below overlap the latency of the loads just issued)
         if (!TMA) {
             // value level slab -> shared memory (interior by cp.async, the one-pixel border zeroed by hand)
@@ -407,14 +422,6 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
                 const int y = (i >> 4) + 1, side = (i >> 3) & 1, c = i & 7;
                 V4[(y * Wp + side * (W + 1)) * 8 + c] = z;
             }
-        }
-        // A unit this CTA owns alone zeroes its own slab of grad_value here, right before it accumulates into it: the lines are
-        // still in L2 when the reductions arrive, and no 42 MB memset runs ahead of the kernel.  (The few leftover units that
-        // several CTAs share lie in the frames >= zero_frames, which the host zeroes with a small memset.)
-        if (!piece && n < sp.zero_frames) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            float *gvl = grad_value + lvl_row;
-            for (int i = tid; i < H * W * 8; i += kThreads) *reinterpret_cast<float4 *>(gvl + (i >> 3) * pix + (i & 7) * 4) = z;
         }
         for (int i = tid; i <= cells; i += kThreads) cell_off[i] = 0;
         for (int c = tid; c < cells; c += kThreads) {

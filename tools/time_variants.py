@@ -31,6 +31,28 @@ def timeit(fn, reps=100, warm=10):
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
 
+def timeit_graph(fn, reps=20):
+    """GPU time without the host in the loop: NS launches captured into one CUDA graph, replayed `reps` times (small N: the Python
+    call + tensor-map encode of an eager launch take longer than the kernel itself)."""
+    fn(*sets[0])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(NS):
+            fn(*sets[i])
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (reps * NS) * 1e3
+
+if os.environ.get("MSDA_GRAPH") == "1":
+    timeit = lambda fn, reps=100, warm=10: timeit_graph(fn)
 f = timeit(lambda v, l, a, g: pkg.ms_deform_attn_forward(v, shapes, start, l, a, 128))
 b = timeit(lambda v, l, a, g: pkg.ms_deform_attn_backward(v, shapes, start, l, a, g, 128))
 peak, _ = load_peaks()
