@@ -32,6 +32,13 @@ EXPORTS = (
     "msda_linear_forward",
     "msda_linear_wgrad_supported",
     "msda_linear_wgrad",
+    "msda_layernorm_supported",
+    "msda_layernorm_backward_workspace_bytes",
+    "msda_add_layernorm_forward",
+    "msda_layernorm_backward",
+    "msda_colsum_supported",
+    "msda_colsum_workspace_bytes",
+    "msda_colsum",
 )
 
 _lib = None
@@ -81,6 +88,20 @@ def load():
     lib.msda_linear_wgrad_supported.restype = i
     lib.msda_linear_wgrad.argtypes = [vp, vp, vp, i, i, i, i, vp]
     lib.msda_linear_wgrad.restype = i
+    lib.msda_layernorm_supported.argtypes = [i]
+    lib.msda_layernorm_supported.restype = i
+    lib.msda_layernorm_backward_workspace_bytes.argtypes = [i, i, i]
+    lib.msda_layernorm_backward_workspace_bytes.restype = sz
+    lib.msda_add_layernorm_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, ctypes.c_float, i, vp]
+    lib.msda_add_layernorm_forward.restype = i
+    lib.msda_layernorm_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, i, i, i, vp]
+    lib.msda_layernorm_backward.restype = i
+    lib.msda_colsum_supported.argtypes = [i]
+    lib.msda_colsum_supported.restype = i
+    lib.msda_colsum_workspace_bytes.argtypes = [i, i, i]
+    lib.msda_colsum_workspace_bytes.restype = sz
+    lib.msda_colsum.argtypes = [vp, vp, vp, sz, i, i, i, vp]
+    lib.msda_colsum.restype = i
     lib.msda_host_pipeline_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), i, i, i]
     lib.msda_host_pipeline_create.restype = i
     lib.msda_host_pipeline_destroy.argtypes = [vp]

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libmsda_b200.so")
-SOURCES = ["msda_api.cu", "msda_generic.cu", "msda_warp32.cu", "msda_slab32.cu", "msda_sorted32.cu", "msda_linear.cu", "msda_host.cu"]
+SOURCES = ["msda_api.cu", "msda_generic.cu", "msda_warp32.cu", "msda_slab32.cu", "msda_sorted32.cu", "msda_linear.cu", "msda_layernorm.cu", "msda_host.cu"]
 HEADERS = ["msda_common.cuh", "msda_kernels.h", "msda_tma.cuh", os.path.join("..", "..", "include", "msda_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

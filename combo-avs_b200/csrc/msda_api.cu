@@ -406,4 +406,97 @@ int msda_linear_wgrad(const void *grad_y, const void *x, void *grad_weight, int 
     return MSDA_OK;
 }
 
+int msda_layernorm_supported(int C) { return layernorm_supported(C) ? 1 : 0; }
+
+size_t msda_layernorm_backward_workspace_bytes(int M, int C, int device)
+{
+    DeviceInfo di;
+    if (M <= 0 || !layernorm_supported(C) || device_info(device, di) != MSDA_OK) return 0;
+    return layernorm_backward_workspace(M, C, di.sm_count);
+}
+
+int msda_add_layernorm_forward(const void *a, const void *b, const void *gamma, const void *beta, void *y, void *mean, void *rstd,
+                               int M, int C, float eps, int device, void *stream)
+{
+    if (M < 0 || !layernorm_supported(C)) return fail(MSDA_ERR_DIM, "msda_add_layernorm_forward needs M >= 0 and C in {128, 256, 384, 512} (M=%d C=%d)", M, C);
+    if (M == 0) return MSDA_OK;
+    if (!a || !gamma || !beta || !y || !mean || !rstd) return fail(MSDA_ERR_NULL, "NULL pointer in msda_add_layernorm_forward");
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) |
+         reinterpret_cast<uintptr_t>(y)) & 15)
+        return fail(MSDA_ERR_DIM, "msda_add_layernorm_forward needs 16-byte aligned pointers");
+    DeviceInfo di;
+    int rc = device_info(device, di);
+    if (rc != MSDA_OK) return rc;
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    e = add_layernorm_forward((const float *)a, (const float *)b, (const float *)gamma, (const float *)beta, (float *)y, (float *)mean, (float *)rstd, M, C,
+                              eps, di.sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "msda_add_layernorm_forward launch");
+    return MSDA_OK;
+}
+
+int msda_layernorm_backward(const void *grad_y, const void *a, const void *b, const void *gamma, const void *mean, const void *rstd,
+                            void *grad_x, void *grad_gamma, void *grad_beta, void *workspace, size_t workspace_bytes,
+                            int M, int C, int device, void *stream)
+{
+    if (M < 0 || !layernorm_supported(C)) return fail(MSDA_ERR_DIM, "msda_layernorm_backward needs M >= 0 and C in {128, 256, 384, 512} (M=%d C=%d)", M, C);
+    if (!grad_gamma || !grad_beta) return fail(MSDA_ERR_NULL, "NULL gradient pointer in msda_layernorm_backward");
+    DeviceInfo di;
+    int rc = device_info(device, di);
+    if (rc != MSDA_OK) return rc;
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (M == 0) {  // no rows: the parameter gradients are zero
+        e = cudaMemsetAsync(grad_gamma, 0, (size_t)C * sizeof(float), (cudaStream_t)stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(grad_beta, 0, (size_t)C * sizeof(float), (cudaStream_t)stream);
+        return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "cudaMemsetAsync(grad_gamma / grad_beta)");
+    }
+    if (!grad_y || !a || !gamma || !mean || !rstd || !grad_x) return fail(MSDA_ERR_NULL, "NULL pointer in msda_layernorm_backward");
+    if ((reinterpret_cast<uintptr_t>(grad_y) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(gamma) |
+         reinterpret_cast<uintptr_t>(grad_x) | reinterpret_cast<uintptr_t>(workspace)) & 15)
+        return fail(MSDA_ERR_DIM, "msda_layernorm_backward needs 16-byte aligned pointers");
+    const size_t need = layernorm_backward_workspace(M, C, di.sm_count);
+    if (!workspace || workspace_bytes < need)
+        return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
+    e = layernorm_backward((const float *)grad_y, (const float *)a, (const float *)b, (const float *)gamma, (const float *)mean, (const float *)rstd,
+                           (float *)grad_x, (float *)grad_gamma, (float *)grad_beta, (float *)workspace, M, C, di.sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "msda_layernorm_backward launch");
+    return MSDA_OK;
+}
+
+int msda_colsum_supported(int N) { return colsum_supported(N) ? 1 : 0; }
+
+size_t msda_colsum_workspace_bytes(int M, int N, int device)
+{
+    DeviceInfo di;
+    if (M <= 0 || !colsum_supported(N) || device_info(device, di) != MSDA_OK) return 0;
+    return colsum_workspace(M, N, di.sm_count);
+}
+
+int msda_colsum(const void *g, void *out, void *workspace, size_t workspace_bytes, int M, int N, int device, void *stream)
+{
+    if (M < 0 || !colsum_supported(N)) return fail(MSDA_ERR_DIM, "msda_colsum needs M >= 0, N %% 4 == 0 and N <= 4096 (M=%d N=%d)", M, N);
+    if (!out) return fail(MSDA_ERR_NULL, "out is NULL");
+    DeviceInfo di;
+    int rc = device_info(device, di);
+    if (rc != MSDA_OK) return rc;
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (M == 0) {
+        e = cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), (cudaStream_t)stream);
+        return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "cudaMemsetAsync(out)");
+    }
+    if (!g) return fail(MSDA_ERR_NULL, "g is NULL");
+    if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(workspace)) & 15) return fail(MSDA_ERR_DIM, "msda_colsum needs 16-byte aligned pointers");
+    const size_t need = colsum_workspace(M, N, di.sm_count);
+    if (!workspace || workspace_bytes < need)
+        return fail(MSDA_ERR_WORKSPACE, "workspace of %zu bytes required, got %zu", need, workspace ? workspace_bytes : (size_t)0);
+    e = colsum((const float *)g, (float *)out, (float *)workspace, M, N, di.sm_count, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "msda_colsum launch");
+    return MSDA_OK;
+}
+
 }  // extern "C"

@@ -66,6 +66,17 @@ bool linear_wgrad_supported(int M, int N, int K);
 cudaError_t linear_tf32(const float *A, const float *W, const float *bias, float *C, int M, int N, int K, int relu, int split, int mn_major,
                         int device, int sm_count, int smem_optin, cudaStream_t st);
 
+// msda_layernorm.cu: y = LayerNorm(a + b) forward / backward and column sums (bias gradients), HBM-bound single-pass kernels
+bool layernorm_supported(int C);
+size_t layernorm_backward_workspace(int M, int C, int sm_count);
+cudaError_t add_layernorm_forward(const float *a, const float *b, const float *gamma, const float *beta, float *y, float *mean, float *rstd,
+                                  int M, int C, float eps, int sm_count, cudaStream_t st);
+cudaError_t layernorm_backward(const float *g, const float *a, const float *b, const float *gamma, const float *mean, const float *rstd, float *dx,
+                               float *dgamma, float *dbeta, float *workspace, int M, int C, int sm_count, cudaStream_t st);
+bool colsum_supported(int N);
+size_t colsum_workspace(int M, int N, int sm_count);
+cudaError_t colsum(const float *g, float *out, float *workspace, int M, int N, int sm_count, cudaStream_t st);
+
 // zero the rows of grad[rows][row_elems] whose mask byte is set (masked_fill backward, ms_deform_attn.py:103-104)
 cudaError_t zero_masked_rows(float *grad, const unsigned char *mask, long long rows, int row_elems, int sm_count, cudaStream_t st);
 // softmax backward over the last L*P entries of every (frame, query, head) row, in place on grad (msda_generic.cu)

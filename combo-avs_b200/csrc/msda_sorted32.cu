@@ -348,7 +348,7 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         // What does not touch shared memory goes BEFORE the barrier that ends the previous unit: the loads of this unit's locations and
         // weights (into registers) and the zeroing of its grad_value slab are issued by every warp as soon as IT has finished its part of
         // the previous walk, so their latency runs under the wait for the slowest group instead of after it (that barrier alone held
-        // 4.5 % of the kernel's stall samples, the location loads' long-scoreboard wait another 4.5 %: profiles/r08c): 177.7 -> 171.7 us.
+        // 4.5 % of the kernel's stall samples, the location loads' long-scoreboard wait another 4.5 %: profiles/r08c_*before_reorder.txt and its source page): 177.7 -> 171.7 us.
         // (Going further -- the per-cell table and the whole counting pass ahead of the barrier too, into a second set of counters --
         // LOSES: 184 us; the early warps' shared-memory atomics and stores compete with the warps that are still walking, and those
         // set the time.  profiles/r08a-f_*, profiles/experiments/r08f_*.patch)

@@ -64,8 +64,8 @@ class TensorCoreLinearFunction(Function):
     def backward(ctx, grad_y):
         x2d, weight, y = ctx.saved_tensors
         g2d = grad_y.reshape(-1, grad_y.shape[-1])
-        if y is not None:
-            g2d = g2d * (y > 0)  # ReLU'
+        if y is not None:  # ReLU': one vectorised pass (a bool mask + a type-promoting multiply are two, the second one unvectorised)
+            g2d = torch.ops.aten.threshold_backward(g2d, y, 0.0)
         g2d = g2d.contiguous()
         grad_x = grad_w = grad_b = None
         if ctx.needs_input_grad[0]:  # dgrad: grad_x[M, K] = g[M, N] @ W[N, K] = linear(g, W^T)
@@ -76,7 +76,8 @@ class TensorCoreLinearFunction(Function):
             else:
                 grad_w = g2d.t() @ x2d
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            grad_b = g2d.sum(0)
+            from .layernorm import column_sum
+            grad_b = column_sum(g2d)
         return grad_x, grad_w, grad_b, None
 
 

@@ -182,6 +182,28 @@ int msda_linear_forward(const void *x, const void *weight, const void *bias, voi
 int msda_linear_wgrad_supported(int M, int N, int K);
 int msda_linear_wgrad(const void *grad_y, const void *x, void *grad_weight, int M, int N, int K, int device, void *stream);
 
+
+/*
+ * Row f2, the elementwise epilogue of the encoder layer's GEMMs -- reference models/modeling/pixel_decoder/msdeformattn.py:119-134:
+ *     src = norm1(src + dropout1(self_attn(...)));   src = norm2(src + dropout2(linear2(...)))        (dropout 0 in COMBO's configs)
+ * i.e. y[M, C] = LayerNorm(a + b) * gamma + beta (torch.nn.LayerNorm semantics: biased variance, eps inside the square root), float32,
+ * row-major, 16-byte aligned, C a multiple of 128 up to 512 (msda_layernorm_supported).  `b` may be NULL (plain LayerNorm).  The forward
+ * saves mean[M] and rstd[M]; the backward recomputes the normalised row from a + b and returns grad_x (the gradient of BOTH a and b),
+ * grad_gamma[C] and grad_beta[C], reduced over the rows in a fixed order (deterministic; scratch of
+ * msda_layernorm_backward_workspace_bytes(M, C, device) bytes from the caller -- the library allocates nothing).
+ * msda_colsum: out[N] = sum over the M rows of g[M, N] -- the bias gradient of a Linear layer (torch: grad_y.sum(0)); N % 4 == 0, N <= 4096.
+ */
+int msda_layernorm_supported(int C);
+size_t msda_layernorm_backward_workspace_bytes(int M, int C, int device);
+int msda_add_layernorm_forward(const void *a, const void *b, const void *gamma, const void *beta, void *y, void *mean, void *rstd,
+                               int M, int C, float eps, int device, void *stream);
+int msda_layernorm_backward(const void *grad_y, const void *a, const void *b, const void *gamma, const void *mean, const void *rstd,
+                            void *grad_x, void *grad_gamma, void *grad_beta, void *workspace, size_t workspace_bytes,
+                            int M, int C, int device, void *stream);
+int msda_colsum_supported(int N);
+size_t msda_colsum_workspace_bytes(int M, int N, int device);
+int msda_colsum(const void *g, void *out, void *workspace, size_t workspace_bytes, int M, int N, int device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
