@@ -60,6 +60,27 @@ def make_inputs(N, shapes, M, D, Lq, P, seed=0, lo=0.0, hi=1.0, dtype=np.float32
                 attn=attn.astype(dtype), grad_out=grad_out.astype(dtype))
 
 
+def rel_err_elementwise(a, b):
+    """max over the elements of |a-b| / |b| -- the strict reading of "relative error"; only meaningful where b has no zero crossings
+    (the forward output on the reference's test distribution: positive values, positive weights)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0 and b.size == 0:
+        return 0.0
+    return float((np.abs(a - b) / np.maximum(np.abs(b), 1e-300)).max())
+
+
+def close_elementwise(a, b, tol):
+    """|a-b| <= tol * (|b| + rms(b)) for every element: relative where the element is large, absolute at the scale of the tensor
+    where it crosses zero (gradients)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if b.size == 0:
+        return a.size == 0
+    rms = float(np.sqrt(np.mean(b * b)))
+    return bool((np.abs(a - b) <= tol * (np.abs(b) + rms)).all())
+
+
 def rel_err(a, b):
     """max-norm relative error: max|a-b| / max|b| (elementwise relative error is meaningless near zero crossings)."""
     a = np.asarray(a, dtype=np.float64)

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import oracle
-from conftest import S4_SHAPES, level_start, load_golden, make_inputs, rel_err
+from conftest import S4_SHAPES, close_elementwise, level_start, load_golden, make_inputs, rel_err, rel_err_elementwise
 
 pytestmark = pytest.mark.gpu
 
@@ -120,6 +120,8 @@ def test_s4_shape_all_variants_fp32(pkg, N):
         out = run_op(pkg, d, backward=False)
         assert pkg.last_variant("forward") == fv
         assert rel_err(out, ref[0]) < 1e-5, fv
+        # the strict reading of north_star's "1e-5 relative": every element, not only the max norm (measured: 1e-6)
+        assert rel_err_elementwise(out, ref[0]) < 1e-5, fv
     pkg.select_variant("forward", "auto")
     for bv in variants(pkg, "backward"):
         pkg.select_variant("backward", bv)
@@ -128,6 +130,8 @@ def test_s4_shape_all_variants_fp32(pkg, N):
         assert rel_err(gv, ref[1]) < 1e-4, bv
         check_grad_loc(gl, ref[2], d, 1e-4)
         assert rel_err(ga, ref[3]) < 1e-4, bv
+        # element by element as well: relative where an element is large, at the tensor's scale where it crosses zero
+        assert close_elementwise(gv, ref[1], 1e-4) and close_elementwise(ga, ref[3], 1e-4), bv
     pkg.select_variant("backward", "auto")
 
 
@@ -232,10 +236,11 @@ def test_query_count_differs_from_value_length(pkg):
 
 
 @pytest.mark.parametrize("loc_dtype", [torch.float32, torch.bfloat16])
-def test_bf16(pkg, loc_dtype):
+@pytest.mark.parametrize("N", [4, 40])
+def test_bf16(pkg, loc_dtype, N):
     """bf16 has no counterpart in the reference (float/double dispatch only, ms_deform_attn_cuda.cu:69); its oracle is
-    the fp64 oracle on the bf16-rounded inputs. north_star: forward within 1e-2."""
-    d = make_inputs(4, S4_SHAPES, 8, 32, 1029, 4, seed=8)
+    the fp64 oracle on the bf16-rounded inputs. north_star: forward within 1e-2.  (A compatibility path: DESIGN.md 5.5.)"""
+    d = make_inputs(N, S4_SHAPES, 8, 32, 1029, 4, seed=8)
     ref = oracle_all(d, torch.bfloat16, loc_dtype)
     out, gv, gl, ga = run_op(pkg, d, torch.bfloat16, loc_dtype)
     assert rel_err(out, ref[0]) < 1e-2
@@ -747,6 +752,8 @@ def test_bench_prints_one_json_line_with_the_contract_keys():
         assert k in d, k
     assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] >= 3 and d["dtype"] == "f32" and d["scaling"] == "weak"
     assert d["value"] > 0 and d["gpu_launches"] == 2 * 5 and "workload" in d["config"]
+    # the K steps are replayed from a CUDA graph (4 captured steps + 1 eager one here); the eager launch loop is reported next to it
+    assert d["launch"].startswith("cuda_graph_replay") and d["eager_launch_loop"]["value"] > 0 and d["eager_launch_loop"]["gpu_launches"] == 2 * 5
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and 0 < rf["frac"] < 1 and abs(rf["achieved"] / rf["peak"] - rf["frac"]) < 1e-9
     e = d["e2e"]
