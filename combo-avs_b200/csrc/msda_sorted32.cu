@@ -351,7 +351,7 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         // 4.5 % of the kernel's stall samples, the location loads' long-scoreboard wait another 4.5 %: profiles/r08c_*before_reorder.txt and its source page): 177.7 -> 171.7 us.
         // (Going further -- the per-cell table and the whole counting pass ahead of the barrier too, into a second set of counters --
         // LOSES: 184 us; the early warps' shared-memory atomics and stores compete with the warps that are still walking, and those
-        // set the time.  profiles/r08a-q_*, profiles/experiments/r08f_*.patch)
+        // set the time.  profiles/r08a-r_*, profiles/experiments/r08f_*.patch)
         // ---- pass 1: cell of every sample of this level, rank inside the cell (shared-memory integer atomics) ----------
         // sample (q, p) of this (n, m, l) sits at loc2[q*qstride + p]; per-unit base pointers keep the index math 32-bit
         const long long meta0 = ((n * Lq) * sp.M + m) * (long long)LP + l * P;
