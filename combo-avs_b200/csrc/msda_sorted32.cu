@@ -553,8 +553,15 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         wa.cinfo_s = cinfo_s;
         wa.V_s = (unsigned)__cvta_generic_to_shared(V4) + chf * 4;
         wa.Wpb = Wp * (kD * 4);
-        wa.e_lo = E0 + E * grp / kGroups;  // E <= 4608, grp < 96: fits 32 bits
-        wa.e_hi = E0 + E * (grp + 1) / kGroups;
+        // Which range a group walks: the r-th of kGroups equal ranges with r = (group within its warp) * (warps) + warp, NOT r = group.
+        // The first and the last row of cells of a level only receive samples from half their area -- twice the cell switches per
+        // sample -- and a warp pays for a switch whenever ANY of its four groups switches: with r = group, warp 0 (ranges 0..3, all in
+        // the first rows) was the last to finish in 52 % of the units and the last warp in 18 %, the others waiting ~10 % of the walk
+        // at the unit barrier (globaltimer stamps per warp, profiles/r08a-r_*).  Transposed, every warp holds at most one such range:
+        // 172.1 -> 170.2 us (N=80: 322.4 -> 318.6).  (Steering those ranges to the high warp ids that the arbiter favours: no further gain.)
+        const int rng = (grp & 3) * (kGroups / 4) + (grp >> 2);
+        wa.e_lo = E0 + E * rng / kGroups;  // E <= 4608, rng < 96: fits 32 bits
+        wa.e_hi = E0 + E * (rng + 1) / kGroups;
         wa.full = E / kGroups;
         wa.gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD + chf;  // grad_out row of query q: gobase + q*pix (this lane's chunk folded in)
         wa.grow_b = (unsigned)pix * (unsigned)sizeof(TV);                  // bytes between the grad_out rows of consecutive queries
