@@ -9,15 +9,15 @@
 //     x * w  ~=  hi_x*hi_w + hi_x*lo_w + lo_x*hi_w            (the dropped lo*lo term is below 2^-21 relative)
 // is accumulated in float32 in tensor memory by three tcgen05.mma.kind::tf32 per 8-wide K step ("3xTF32").
 //
-// Kernel (one persistent CTA per SM, warp-specialised, 320 threads):
+// Kernel (one persistent CTA per SM, warp-specialised, 448 threads):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled boxes of A [128 x 32] and W [BN x 32] into a ring of stages
-//   warps 2-5   splitters: when a stage has landed, write lo = x - trunc_tf32(x) next to it (shared memory only; kind::tf32 ignores the
+//   warps 2-9   splitters: when a stage has landed, write lo = x - trunc_tf32(x) next to it (shared memory only; kind::tf32 ignores the
 //               13 low mantissa bits of its operands -- measured -- so the raw tile already is `hi`), fence.proxy.async, hand the stage to
 //   warp 1      the MMA issuer: one elected lane issues 3 x 4 tcgen05.mma (M=128, N=BN<=128, K=8) per stage -- hi*hi into one TMEM
 //               accumulator, hi*lo + lo*hi into a second one (the tensor core truncates when it aligns addends; kept apart, the small
 //               cross terms are truncated at their own magnitude and the large accumulator sees a third of the additions);
 //               tcgen05.commit releases the stage to the producer and, after the last K block, the accumulators to
-//   warps 6-9   the epilogue: tcgen05.ld both accumulators (lane = row), add them, the bias (from shared memory) and optionally ReLU or a
+//   warps 10-13 the epilogue: tcgen05.ld both accumulators (lane = row), add them, the bias (from shared memory) and optionally ReLU or a
 //               ReLU' mask, transpose 32 x 32 blocks through a padded staging tile and write 128 contiguous bytes per row (a direct
 //               row store touches 32 lines with 16 bytes each: measured 143 us for the stores alone); the next tile's accumulators
 //               (the other 256 TMEM columns) are being filled meanwhile.
@@ -40,8 +40,9 @@ namespace {
 constexpr int kBM = 128;          // rows of A per tile = TMEM lanes
 constexpr int kBK = 32;           // floats per K block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;         // K of one tcgen05.mma.kind::tf32
-constexpr int kThreads = 320;
-constexpr int kSplitWarp0 = 2, kEpiWarp0 = 6;
+constexpr int kSplitters = 8;  // splitter warps (4 / 8 / 12 / 16: 164 / 137 / 140 / 141 us on 41160 x 256 x 1024, profiles/r08vw_linear_splitters.txt)
+constexpr int kSplitWarp0 = 2, kEpiWarp0 = kSplitWarp0 + kSplitters;
+constexpr int kThreads = (kEpiWarp0 + 4) * 32;
 constexpr int kStagePitch = 36;   // floats per staged row: 32 columns + 4 of padding (16-byte aligned, conflict-free both ways)
 constexpr int kBiasFloats = 2048;
 
@@ -170,7 +171,7 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
     if (threadIdx.x == 0) {
         for (int s = 0; s < lp.stages; ++s) {
             mbar_init(full(s), 1);
-            mbar_init(ready(s), 4);   // one arrival per splitter warp
+            mbar_init(ready(s), kSplitters);   // one arrival per splitter warp
             mbar_init(empty(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -259,7 +260,7 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
     } else if (wid < kEpiWarp0) {
         // ---- splitters: x -> (hi, lo) in shared memory --------------------------------------------------------------------------
         if (lp.split) {
-            const int st = threadIdx.x - kSplitWarp0 * 32;  // 0..127
+            const int st = threadIdx.x - kSplitWarp0 * 32;  // 0..32*kSplitters-1
             int it = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 int tm, tn, kb0, kblocks;
@@ -272,14 +273,14 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
                     float4 *hi = reinterpret_cast<float4 *>(base);
                     float4 *lo = reinterpret_cast<float4 *>(base + hi_bytes);
                     const unsigned n16 = hi_bytes / 16;  // four 16-byte chunks per thread per round: the loads of a round go out together
-                    for (unsigned i0 = st; i0 < n16; i0 += 4 * 128) {
+                    for (unsigned i0 = st; i0 < n16; i0 += 4 * (kSplitters * 32)) {
                         float4 x[4];
 #pragma unroll
                         for (int r = 0; r < 4; ++r)
-                            if (i0 + r * 128 < n16) x[r] = hi[i0 + r * 128];
+                            if (i0 + r * (kSplitters * 32) < n16) x[r] = hi[i0 + r * (kSplitters * 32)];
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
-                            if (i0 + r * 128 >= n16) break;
+                            if (i0 + r * (kSplitters * 32) >= n16) break;
                             // kind::tf32 ignores the 13 low mantissa bits of its operands (measured, profiles/r05_linear_tcgen05.txt): the raw
                             // float32 tile already IS the hi operand; only lo = x - trunc(x) (exact in float32) is written
                             float4 l;
@@ -287,7 +288,7 @@ linear_tf32_kernel(const float *__restrict__ bias, float *__restrict__ C, const 
                             l.y = x[r].y - __uint_as_float(__float_as_uint(x[r].y) & 0xffffe000u);
                             l.z = x[r].z - __uint_as_float(__float_as_uint(x[r].z) & 0xffffe000u);
                             l.w = x[r].w - __uint_as_float(__float_as_uint(x[r].w) & 0xffffe000u);
-                            lo[i0 + r * 128] = l;
+                            lo[i0 + r * (kSplitters * 32)] = l;
                         }
                     }
                     fence_proxy_async();  // these generic-proxy writes are read by the tensor core (async proxy)
