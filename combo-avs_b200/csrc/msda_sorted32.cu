@@ -120,8 +120,9 @@ struct WalkArgs {
     unsigned ent_s, cinfo_s, V_s;  // shared-memory byte addresses: sorted entries, per-cell table, value slab (+ this lane's chunk)
     int Wpb;                       // bytes per row of the padded slab
     int e_lo, e_hi, full;          // this group's entries; `full` = entries every group owns (the others own one more)
-    const void *gobase;            // grad_out row 0 of this (frame, head), this lane's chunk
+    const void *gobase;            // grad_out row 0 of this (frame, head): the same for every lane (a uniform register pair)
     unsigned grow_b;               // bytes between grad_out rows of consecutive queries
+    unsigned glane_b;              // byte offset of this lane's chunk inside a row
     float *gbase;                  // grad_value pixel (0, 0) of this (frame, head, level), this lane's chunk
     int o01, o10;                  // grad_value element offsets of the right / lower neighbour
     void *res_base;                // where this lane's result of a sample goes (grad_attn, grad_loc.y or grad_loc.x; lanes 3..7: unused)
@@ -136,7 +137,7 @@ __device__ __forceinline__ void walk_range(const WalkArgs &wa)
     const unsigned ent_s = wa.ent_s, cinfo_s = wa.cinfo_s, V_s = wa.V_s;
     const int Wpb = wa.Wpb, e_lo = wa.e_lo, e_hi = wa.e_hi, qs = wa.qs, j = wa.j;
     const TV *gobase = reinterpret_cast<const TV *>(wa.gobase);
-    const unsigned grow_b = wa.grow_b;
+    const unsigned grow_b = wa.grow_b, glane_b = wa.glane_b;
     float *gbase = wa.gbase;
     const int o01 = wa.o01, o10 = wa.o10, o11 = wa.o01 + wa.o10;
     TM *res_base = reinterpret_cast<TM *>(wa.res_base);
@@ -171,16 +172,27 @@ __device__ __forceinline__ void walk_range(const WalkArgs &wa)
         unsigned packed;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(packed) : "r"(ent_s + e2 * 16 + 12));
         // 64-bit base + unsigned 32-bit byte offset: two adds instead of a sign-extended 64-bit multiply-shift chain
-        const TV *gq = reinterpret_cast<const TV *>(reinterpret_cast<const char *>(gobase) + (packed & 0xffff) * grow_b);
+        // uniform 64-bit base + 32-bit (row * pitch + lane chunk): one multiply-add and one 64-bit add per load
+        const TV *gq = reinterpret_cast<const TV *>(reinterpret_cast<const char *>(gobase) + ((packed & 0xffff) * grow_b + glane_b));
         g = load4(gq);
     };
     // s_h / s_w arrive already multiplied by the sample's attention weight (cuh:126-127), so the tail is one multiply per lane
+    // lane-dependent selects of the butterfly as ONE bitwise instruction each on a mask kept in a register: as predicates, j & 1 and
+    // j & 2 were re-derived in every step (three instructions; there are only seven predicate registers)
+    unsigned m1 = (j & 1) ? 0xffffffffu : 0u, m2 = (j & 2) ? 0xffffffffu : 0u;
+    pin(m1);
+    pin(m2);
+    auto pick = [](unsigned m, float if_set, float if_clear) {
+        unsigned r;
+        asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(m), "r"(__float_as_uint(if_set)), "r"(__float_as_uint(if_clear)));
+        return __uint_as_float(r);
+    };
     auto finish = [&](float s_a, float s_h, float s_w, int sidx) {  // transposed butterfly + stores
-        float x = (j & 1) ? s_h : s_a;
-        x += __shfl_xor_sync(0xffffffffu, (j & 1) ? s_a : s_h, 1);
+        float x = pick(m1, s_h, s_a);
+        x += __shfl_xor_sync(0xffffffffu, pick(m1, s_a, s_h), 1);
         s_w += __shfl_xor_sync(0xffffffffu, s_w, 1);
-        float keep = (j & 2) ? s_w : x;
-        keep += __shfl_xor_sync(0xffffffffu, (j & 2) ? x : s_w, 2);
+        float keep = pick(m2, s_w, x);
+        keep += __shfl_xor_sync(0xffffffffu, pick(m2, x, s_w), 2);
         keep += __shfl_xor_sync(0xffffffffu, keep, 4);
         if (sidx >= 0 && j < 3) store1(res_base + sidx * res_stride, keep * res_scale);
     };
@@ -563,8 +575,9 @@ bwd_sorted32_kernel(const TV *__restrict__ value, const TM *__restrict__ loc, co
         wa.e_lo = E0 + E * rng / kGroups;  // E <= 4608, rng < 96: fits 32 bits
         wa.e_hi = E0 + E * (rng + 1) / kGroups;
         wa.full = E / kGroups;
-        wa.gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD + chf;  // grad_out row of query q: gobase + q*pix (this lane's chunk folded in)
+        wa.gobase = grad_out + (n * Lq * sp.M + m) * (long long)kD;       // grad_out row of query q: gobase + q*pix
         wa.grow_b = (unsigned)pix * (unsigned)sizeof(TV);                  // bytes between the grad_out rows of consecutive queries
+        wa.glane_b = (unsigned)chf * (unsigned)sizeof(TV);
         wa.gbase = grad_value + lvl_row + chf;
         wa.o01 = pix;
         wa.o10 = W * pix;
