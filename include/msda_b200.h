@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define MSDA_VERSION 100 /* major*100 + minor */
+#define MSDA_VERSION 102 /* major*100 + minor: 1.0 the op, 1.1 + msda_linear_*, 1.2 + msda_add_layernorm_* / msda_colsum */
 
 /* element types */
 #define MSDA_F32 0

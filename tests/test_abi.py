@@ -34,7 +34,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_version_and_variants(lib):
     L = lib.load()
-    assert L.msda_version() == 100
+    assert L.msda_version() == 102
     assert "auto" in lib.variant_names("forward") and "generic" in lib.variant_names("backward")
     assert L.msda_select_variant(0, b"no-such-kernel") == -5
     assert b"unknown forward variant" in L.msda_last_error()
