@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """GPU experiment: time the sorted32 backward on a pyramid whose slabs are small (three 14 x 14 levels, 588 queries), so that the
 kernel's own shared memory is ~83 KB and MSDA_SORTED_SMEM_EXTRA (set by the caller) decides the L1 size: how does the walk depend on it?
+(The switch -- extra dynamic shared memory added to the launch -- existed only in the experimental build of round 2, kept as
+profiles/experiments/r07_*.patch; with the shipped library this script times the small pyramid as is.  Results: DESIGN.md 5.7, r07p.)
 usage: python tools/l1_probe.py [frames]"""
 import os, sys
 import torch
