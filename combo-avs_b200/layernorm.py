@@ -9,6 +9,7 @@ import ctypes
 
 import torch
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 from .functions import _ptr
@@ -52,6 +53,7 @@ class AddLayerNormFunction(Function):
         return y.view(a.shape)
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_y):
         a2, b2, w, stats = ctx.saved_tensors
         m, c = a2.shape
