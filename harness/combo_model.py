@@ -258,16 +258,23 @@ class ComboR50(nn.Module):
     (:335-352), frozen VGGish (:327-330), MaskFormerHead = product pixel decoder -> late AVFuse on the mask features -> audio MLP ->
     masked transformer decoder (mask_former_head.py:141-159)."""
 
-    def __init__(self, num_classes=2, num_frames=5):
+    def __init__(self, num_classes=2, num_frames=5, backbone="r50"):
+        """backbone: "r50" (configs/avs_s4, avs_ms3 R50 settings) or "pvtv2_b5" (BASELINE configs 4 / 5: harness/pvtv2.py; the pre-mask
+        branch uses the same backbone type, PRE_SAM_DIM [64, 128, 320, 512]).  num_classes 2 (S4 / MS3: background + object), 71 (AVSS)."""
         super().__init__()
         self.num_frames = num_frames
-        self.backbone = ResNet50Features()
-        self.pre_sam_backbone = ResNet50Features()
-        self.scale_factor_module = nn.ModuleList(ChannelGate(c) for c, _ in R50_FEATURES.values())
+        if backbone == "pvtv2_b5":
+            from .pvtv2 import PVTV2_B5_FEATURES, PVTv2B5Features
+            features, make = PVTV2_B5_FEATURES, PVTv2B5Features
+        else:
+            features, make = R50_FEATURES, ResNet50Features
+        self.backbone = make()
+        self.pre_sam_backbone = make()
+        self.scale_factor_module = nn.ModuleList(ChannelGate(c) for c, _ in features.values())
         self.audio_backbone = VGGish()
         for p in self.audio_backbone.parameters():
             p.requires_grad = False
-        self.pixel_decoder = MSDeformAttnPixelDecoder(R50_FEATURES, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
+        self.pixel_decoder = MSDeformAttnPixelDecoder(features, transformer_dropout=0.0, transformer_nheads=8, transformer_dim_feedforward=1024,
                                                       transformer_enc_layers=6, conv_dim=256, mask_dim=256, norm="GN",
                                                       transformer_in_features=["res3", "res4", "res5"], common_stride=4)
         self.fusion_module = AVFuse(256, 128, 8)
@@ -312,7 +319,7 @@ def clip_full_model_gradients(model, max_norm=0.01):
     return torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.grad is not None], max_norm, foreach=True)
 
 
-def synthetic_clips(n_clips, num_frames=5, size=224, device="cpu", seed=0, supervised_frames=1):
+def synthetic_clips(n_clips, num_frames=5, size=224, device="cpu", seed=0, supervised_frames=1, num_classes=2):
     """AVSBench-shaped synthetic batch (maskformer_model.py:316-323): uint8-range frames and SAM pre-masks, VGGish log-mel patches, and
     ground truth for the supervised frames only -- S4 supervises the FIRST frame of each clip (register_avss4_sem.py:18,49;
     criterion.py:241-254), MS3 all five.  Each supervised frame carries a background (label 0) and an object (label 1) mask."""
@@ -326,5 +333,6 @@ def synthetic_clips(n_clips, num_frames=5, size=224, device="cpu", seed=0, super
         cy, cx, r = (torch.rand(3, generator=g) * torch.tensor([size, size, size / 3.0]) + torch.tensor([0.0, 0.0, size / 8.0])).tolist()
         yy, xx = torch.meshgrid(torch.arange(size), torch.arange(size), indexing="ij")
         obj = ((yy - cy) ** 2 + (xx - cx) ** 2 < r * r)
-        targets.append({"labels": torch.tensor([0, 1], device=device), "masks": torch.stack([~obj, obj]).to(device)})
+        label = 1 if num_classes <= 2 else int(torch.randint(1, num_classes, (1,), generator=g))
+        targets.append({"labels": torch.tensor([0, label], device=device), "masks": torch.stack([~obj, obj]).to(device)})
     return images, pre_masks, audio, targets

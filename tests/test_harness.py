@@ -120,3 +120,29 @@ def test_combo_r50_training_step_runs_on_the_product_kernels():
     assert all(np.isfinite(losses))
     assert pkg.launch_count() - before >= 2 * 6 * 2        # six deformable-attention layers, forward + backward, two steps
     assert pkg.last_variant("forward").startswith("slab32") and pkg.last_variant("backward").startswith("sorted32")
+
+
+def test_pvtv2_b5_backbone_pyramid_and_avss_criterion_on_cpu():
+    """BASELINE configs 4 / 5 (harness only): the PVTv2-B5 pyramid has the channels / strides the pixel decoder is built for
+    (PRE_SAM_DIM [64, 128, 320, 512]), and the criterion takes the AVSS setting -- 71 classes, every frame of a 10-frame clip supervised."""
+    from harness.combo_model import synthetic_clips
+    from harness.criterion import SetCriterion
+    from harness.pvtv2 import PVTV2_B5_FEATURES, PVTv2B5Features
+    net = PVTv2B5Features(depths=(1, 1, 2, 1)).eval()  # (the full depths 3/6/40/3 only change the running time)
+    with torch.no_grad():
+        feats = net(torch.randn(2, 3, 64, 96))
+    for name, (channels, stride) in PVTV2_B5_FEATURES.items():
+        assert feats[name].shape == (2, channels, 64 // stride, 96 // stride), name
+    assert sum(p.numel() for p in PVTv2B5Features().parameters()) == 81443008  # PVTv2-B5 without its classifier head
+    clips, frames, Q, classes = 1, 10, 5, 71
+    _, _, _, targets = synthetic_clips(clips, num_frames=frames, size=32, seed=2, supervised_frames=frames, num_classes=classes)
+    assert len(targets) == frames and all(1 <= int(t["labels"][1]) < classes for t in targets)
+    g = torch.Generator().manual_seed(0)
+    mk = lambda *s: torch.randn(*s, generator=g).requires_grad_(True)
+    sets = [{"pred_logits": mk(frames, Q, classes + 1), "pred_masks": mk(frames, Q, 8, 8)} for _ in range(2)]
+    out = {"pred_logits": sets[-1]["pred_logits"], "pred_masks": sets[-1]["pred_masks"], "aux_outputs": sets[:-1],
+           "middles_attn_mask": [s["pred_masks"].reshape(frames, Q, -1) for s in sets[:-1]]}
+    loss = SetCriterion(num_classes=classes, num_points=64, num_frames=frames)(out, targets)
+    assert torch.isfinite(loss)
+    loss.backward()
+    assert all(out["pred_masks"].grad[f].abs().sum() > 0 for f in range(frames))  # every frame is supervised

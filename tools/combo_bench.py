@@ -1,11 +1,14 @@
 #!/usr/bin/env python
 """COMBO-R50 S4 model-level measurements with the product's pixel decoder on the hot path (harness/: SURVEY.md 8 f3 / f4).
 
-  python tools/combo_bench.py train [clips_per_gpu=8] [iters=8] [strong]   # GPU(s): full training step, DDP under torchrun
+  python tools/combo_bench.py train [clips_per_gpu=8] [iters=8] [strong] [pvt] [ms3|avss]   # GPU(s): full training step, DDP under torchrun
   python tools/combo_bench.py cpu-forward [clips=1]                        # BASELINE config 1: eval forward on the host CPU
 
 train: forward + matcher + criterion + backward + full-model gradient clipping (0.01) + AdamW (train_net.py:147-226), fp32 (AMP is
 off for S4: configs/avs_s4/R50-AVSS4-SemanticSegmentation.yaml:44-45), 5-frame 224x224 synthetic clips, first frame supervised.
+`pvt` swaps both backbones for PVTv2-B5 (harness/pvtv2.py); `ms3` supervises all five frames (BASELINE config 4); `avss` is config 5:
+71 classes, 10-frame clips, every frame supervised, fp16 autocast + GradScaler around the step (AMP is on for AVSS:
+configs/avs_ss/PVT-AVSS-SemanticSegmentation.yaml:41-42) while the pixel decoder keeps float32 (msdeformattn.py:315,321).
 Under torchrun every rank runs its own clips (weak) or, with `strong`, its shard of a global batch of 8 clips (train_net.py:117).
 cpu-forward: the same model on the CPU with the hot path served by the reference's CPU implementation (ms_deform_attn_core_pytorch,
 restated in oracle/core_pytorch.py) -- a BASELINE measurement, which is why this tool (and nothing in the product) touches oracle/."""
@@ -22,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def train(clips, iters, strong):
+def train(clips, iters, strong, backbone="r50", task="s4"):
     import combo_avs_b200 as pkg
     from combo_avs_b200.sharding import max_over_ranks, shard_clips
     from harness.combo_model import ComboR50, build_optimizer, clip_full_model_gradients, synthetic_clips
@@ -32,28 +35,37 @@ def train(clips, iters, strong):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    frames_per_clip = 10 if task == "avss" else 5
+    num_classes = 71 if task == "avss" else 2
+    supervised = 1 if task == "s4" else frames_per_clip
+    amp = task == "avss"
     if strong:
-        clips = shard_clips(8, 5, rank, world)[1] // 5
+        clips = shard_clips(8, frames_per_clip, rank, world)[1] // frames_per_clip
     torch.manual_seed(7)
-    model = ComboR50().to(dev).train()
-    criterion = SetCriterion().to(dev)
+    model = ComboR50(num_classes=num_classes, num_frames=frames_per_clip, backbone=backbone).to(dev).train()
+    criterion = SetCriterion(num_classes=num_classes, num_frames=frames_per_clip).to(dev)
+    scaler = torch.amp.GradScaler("cuda", enabled=amp)
     ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
     opt = build_optimizer(model)
-    images, pre_masks, audio, targets = synthetic_clips(clips, device=dev, seed=100 + rank)
+    images, pre_masks, audio, targets = synthetic_clips(clips, num_frames=frames_per_clip, device=dev, seed=100 + rank,
+                                                        supervised_frames=supervised, num_classes=num_classes)
     times = {}
 
     def step(record=False):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
         opt.zero_grad(set_to_none=True)
         if record: ev[0].record()
-        out = ddp(images, pre_masks, audio)
-        if record: ev[1].record()
-        loss = criterion(out, targets)
+        with torch.autocast("cuda", dtype=torch.float16, enabled=amp):
+            out = ddp(images, pre_masks, audio)
+            if record: ev[1].record()
+            loss = criterion(out, targets)
         if record: ev[2].record()
-        loss.backward()
+        scaler.scale(loss).backward()
         if record: ev[3].record()
+        scaler.unscale_(opt)
         clip_full_model_gradients(model, 0.01)
-        opt.step()
+        scaler.step(opt)
+        scaler.update()
         if record:
             ev[4].record()
             torch.cuda.synchronize()
@@ -79,8 +91,10 @@ def train(clips, iters, strong):
     launches = (pkg.launch_count() - l0) / iters
     for _ in range(3):
         step(record=True)
-    frames = (40 if strong else world * clips * 5)
-    res = {"workload": "COMBO-R50 S4 training step (harness/ + product pixel decoder), fp32, 5-frame 224x224 synthetic clips, first frame supervised",
+    frames = (8 * frames_per_clip if strong else world * clips * frames_per_clip)
+    res = {"workload": "COMBO-%s %s training step (harness/ + product pixel decoder), %s, %d-frame 224x224 synthetic clips, %s supervised" % (
+               "PVTv2-B5" if backbone == "pvtv2_b5" else "R50", task.upper(), "fp16 autocast (pixel decoder fp32)" if amp else "fp32", frames_per_clip,
+               "first frame" if supervised == 1 else "every frame"),
            "n_gpus": world, "scaling": "strong (global batch 8 clips)" if strong else "weak (%d clips per GPU)" % clips,
            "clips_per_gpu": clips, "global_frames": frames, "ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3),
            "loss": float(loss), "msda_launches_per_step": launches,
@@ -134,4 +148,6 @@ if __name__ == "__main__":
     if mode == "cpu-forward":
         cpu_forward(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
     else:
-        train(int(sys.argv[2]) if len(sys.argv) > 2 else 8, int(sys.argv[3]) if len(sys.argv) > 3 else 8, "strong" in sys.argv[4:])
+        flags = sys.argv[4:]
+        train(int(sys.argv[2]) if len(sys.argv) > 2 else 8, int(sys.argv[3]) if len(sys.argv) > 3 else 8, "strong" in flags,
+              backbone="pvtv2_b5" if "pvt" in flags else "r50", task="avss" if "avss" in flags else "ms3" if "ms3" in flags else "s4")
